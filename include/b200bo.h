@@ -1,0 +1,134 @@
+/*
+ * b200bo — C ABI of the B200-native engine for the data-parallel hot path of
+ * IDEALLab/JMD-Diversity-in-Bayesian-Optimization.
+ *
+ * The reference is pure Python and has no FFI of its own; every entry point below
+ * names the reference call site it replaces (file:line under /root/reference).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in _h (host);
+ *  - the caller owns every buffer; the library allocates nothing persistent;
+ *  - calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
+ *    legacy default stream), re-entrant and CUDA-graph capturable;
+ *  - return 0 = OK, < 0 = argument error (nothing launched), > 0 = cudaError_t;
+ *    b200bo_last_error_string() describes the last non-zero return of this thread;
+ *  - numerical failures are per trial in status[] (B200BO_ST_* bits), never a return code.
+ *
+ *  theta = (noise sigma^2, mean constant c, outputscale s, lengthscale l), ACTUAL
+ *  values (the Python layer applies gpytorch's softplus to raw_outputscale /
+ *  raw_lengthscale; noise is untransformed, BO.py:33-68 + SURVEY.md A.1).
+ */
+#ifndef B200BO_H
+#define B200BO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200BO_KERNEL_RBF 0
+#define B200BO_KERNEL_MATERN12 1
+#define B200BO_KERNEL_MATERN32 2
+#define B200BO_KERNEL_MATERN52 3
+
+#define B200BO_ACQ_EI 0
+#define B200BO_ACQ_UCB 1
+#define B200BO_ACQ_PI 2
+
+#define B200BO_ST_JITTER 1      /* Cholesky needed diagonal jitter (psd_safe_cholesky) */
+#define B200BO_ST_CHOL_FAIL 2   /* Cholesky failed after 3 jitter levels              */
+#define B200BO_ST_NONFINITE 4   /* NaN / +inf acquisition value seen                   */
+#define B200BO_ST_ALL_MASKED 8  /* no selectable candidate                             */
+#define B200BO_ST_OFF_LATTICE 16 /* lattice path given an off-lattice observation      */
+
+#define B200BO_NMAX 128         /* max observations per trial in the GP kernels        */
+
+const char* b200bo_version(void);
+const char* b200bo_last_error_string(void);
+/* sm_count / cc of the current device; returns cudaError_t */
+int b200bo_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- K-D  ranked-DPP set score -------------------------------------------------
+ * replaces diverse_data_generator.twoD_score looped over the superset,
+ * Src/data_gen.py:484-497 called from :403.
+ * pool (P,2) f64; idx (N,k) int32 rows index pool; logdet (N) f64 out.
+ * logdet[i] = log det exp(-gamma * D), D_ab = (sqrt(|x_a-x_b|^2))^2; NaN if not PD. */
+int b200bo_dpp_logdet_score(const double* pool, int pool_size, const int32_t* idx, long long N, int k,
+                            double gamma, double* logdet, void* stream);
+
+/* mean / population-sd / z-scores of the scoring block of sub_dpp, data_gen.py:406-408.
+ * stats (2) f64 out = {mean, sd}; z (N) f64 out; ws: >= b200bo_dpp_stats_workspace_bytes(N). */
+size_t b200bo_dpp_stats_workspace_bytes(long long N);
+int b200bo_dpp_zscore(const double* logdet, long long N, double* stats, double* z, void* ws, size_t ws_bytes,
+                      void* stream);
+
+/* ---- K-E  Wildcat Wells --------------------------------------------------------
+ * replaces objectives.wildcatwells (Src/objectives.py:107-218, N = 1 peak, d = 2) and the
+ * 10 201 x 3 SimplexNoise.simplexNoise calls inside it (Src/SimpleNoise.py:85-172).
+ * Per surface s: hseed[s] = randHash(seed) (SimpleNoise.py:20), vecs (S,4,2) int8 = the
+ * gradient table shuffled by random.Random(hseed) (SimpleNoise.py:81-83; 4 entries, host),
+ * peak_xy (S,2) f64 (objectives.py:139-149), smooth / rug_amp (S) f64.
+ * surf (S,101,101) f32 out, row-major [iy][ix], max == 100. */
+int b200bo_wildcat_surface(const uint64_t* hseed, const int8_t* vecs, const double* peak_xy, const double* smooth,
+                           const double* rug_amp, float* surf, int S, void* stream);
+/* raw simplex noise at M points (M,2) f64 for one (hseed, vecs): SimpleNoise.py:85-172 */
+int b200bo_simplex_noise(uint64_t hseed, const int8_t* vecs_h, const double* xy, double* out, long long M,
+                         void* stream);
+
+/* ---- K-A  kernel matrix + Cholesky --------------------------------------------
+ * replaces gpytorch ScaleKernel(Matern|RBF) + psd_safe_cholesky + the prediction-strategy
+ * caches built by SingleTaskGP (BO.py:65,142,176).
+ * X (T,n_max,2) f64, y (T,n_max) f64, n (T) int32 (n[t] <= n_max <= B200BO_NMAX),
+ * theta (T,4) f64.  Outputs (any may be NULL): L (T,n_max,n_max) lower, row-major;
+ * Linv (T,n_max,n_max) = L^-1; alpha (T,n_max) = Khat^-1 (y - c); logdet (T) = log|Khat|;
+ * wfrag (T, b200bo_wfrag_doubles(n_max)) = L^-1 in the MMA-fragment layout K-B consumes.
+ * status (T) int32 is OR-ed into. */
+size_t b200bo_wfrag_doubles(int n_max);
+int b200bo_gp_assemble_chol(const double* X, const double* y, const int32_t* n, const double* theta, double* L,
+                            double* Linv, double* alpha, double* logdet, double* wfrag, int32_t* status, int T,
+                            int n_max, int kernel_id, void* stream);
+
+/* ---- K-B  fused grid posterior + acquisition + arg-max --------------------------
+ * replaces ExpectedImprovement(model,best_f) + optimize_acqf over the box (BO.py:158-161,
+ * 72-83) by a dense arg-max over the candidate grid (the north-star redesign).
+ * grid (G,2) f64 candidates; for trial t: mu = c + k*^T alpha, var = s - |L^-1 k*|^2,
+ * acq = EI/UCB/PI(mu, max(var,var_floor), best_f[t]); candidates with r^2 == 0 to an
+ * observation are masked when mask_observed != 0; extra_mask (G) uint8 optional (shared).
+ * arg_idx (T) int32 / arg_val (T) f64 out: first index of the maximum, -1 if none.
+ * Optional debug fields mu/var/acq (T,G) f64 (NULL to skip).
+ * ws: >= b200bo_grid_acq_workspace_bytes(T, G). */
+size_t b200bo_grid_acq_workspace_bytes(int T, int G);
+int b200bo_grid_posterior_acq_argmax(const double* grid, int G, const double* X, const double* wfrag,
+                                     const double* alpha, const int32_t* n, const double* theta,
+                                     const double* best_f, const uint8_t* extra_mask, int mask_observed,
+                                     int acq_id, double acq_param, double var_floor, int32_t* arg_idx,
+                                     double* arg_val, double* mu, double* var, double* acq, int32_t* status,
+                                     int T, int n_max, int kernel_id, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- K-C  marginal log-likelihood value and gradient ----------------------------
+ * replaces ExactMarginalLogLikelihood + autograd inside fit_gpytorch_model (BO.py:144,189).
+ * raw (T,4) f64 = (noise, c, raw_outputscale, raw_lengthscale); value (T) f64 =
+ * [log N(y; c, Khat) + log Gamma(noise; 1.1, 0.05)] / n ; grad (T,4) f64. */
+int b200bo_mll_value_grad(const double* X, const double* y, const int32_t* n, const double* raw, double* value,
+                          double* grad, int32_t* status, int T, int n_max, int kernel_id, void* stream);
+
+/* ---- batched BO loop bookkeeping (one thread per trial) ---------------------------
+ * replaces the Python statements between two acquisitions in BOloop / BOloop_fixparam:
+ * objective look-up (Src/BO.py:104), append (:164-165), yopt / yall.append (:168-169),
+ * stop test (:152,241) and the post-loop padding of yall to max_iter+2 (:262,267-271).
+ * State: X (T,n_max,2), y (T,n_max), n (T) int32 (n < 0 = finished, |n| observations),
+ * best_f (T), yall (T,max_iter+2), picked (T,max_iter) int32 (-1 = none), nit (T) int32.
+ * obj (S,G) f32 = objective at every candidate for S surfaces; surf_id (T) int32. */
+int b200bo_bo_init(const double* y, int32_t* n, double* best_f, double* yall, int32_t* picked, int32_t* nit, int T,
+                   int n_max, int max_iter, double tol, double optimal_y, void* stream);
+int b200bo_bo_update(const double* grid, int G, const float* obj, const int32_t* surf_id, const int32_t* arg_idx,
+                     double* X, double* y, int32_t* n, double* best_f, double* yall, int32_t* picked, int32_t* nit,
+                     int T, int n_max, int max_iter, int iter, double tol, double optimal_y, void* stream);
+int b200bo_bo_finalize(double* yall, const int32_t* nit, int32_t* n, int T, int max_iter, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200BO_H */

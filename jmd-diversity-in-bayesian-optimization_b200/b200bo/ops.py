@@ -1,0 +1,206 @@
+"""Tensor-level wrappers of the C ABI: one Python function per entry point.
+
+Every function takes CUDA tensors (contiguous, documented dtype), launches on torch's current
+stream and returns tensors.  No CPU implementation exists: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+RBF, MATERN12, MATERN32, MATERN52 = 0, 1, 2, 3
+EI, UCB, PI = 0, 1, 2
+ST_JITTER, ST_CHOL_FAIL, ST_NONFINITE, ST_ALL_MASKED, ST_OFF_LATTICE = 1, 2, 4, 8, 16
+NMAX = 128
+VAR_FLOOR = 1e-9          # botorch 0.8.0 analytic EI clamp
+
+
+def _cu(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.B200boError(f"{name}: expected a CUDA tensor (the engine has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.B200boError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.B200boError(f"{name}: tensor must be contiguous")
+    return t
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def kernel_id_from(nu=2.5, covar="matern") -> int:
+    """Src/BO.py:133-134 (nu > 2.5 switches to RBF) and :61-64."""
+    if covar == "rbf" or nu > 2.5:
+        return RBF
+    try:
+        return {0.5: MATERN12, 1.5: MATERN32, 2.5: MATERN52}[float(nu)]
+    except KeyError:
+        raise ValueError(f"nu={nu}: gpytorch's MaternKernel supports 0.5, 1.5, 2.5") from None
+
+
+# ------------------------------------------------------------------ K-D
+
+def dpp_logdet_score(pool: torch.Tensor, idx: torch.Tensor, gamma: float) -> torch.Tensor:
+    """log det exp(-gamma D) per index set; pool (P,2) f64, idx (N,k) int32 -> (N,) f64."""
+    lib = _lib.load()
+    _cu(pool, torch.float64, "pool")
+    _cu(idx, torch.int32, "idx")
+    if pool.dim() != 2 or pool.shape[1] != 2 or idx.dim() != 2:
+        raise _lib.B200boError("dpp_logdet_score: pool must be (P,2), idx (N,k)")
+    N, k = idx.shape
+    out = torch.empty(N, dtype=torch.float64, device=pool.device)
+    check(lib.b200bo_dpp_logdet_score(_ptr(pool), pool.shape[0], _ptr(idx), N, k, float(gamma), _ptr(out), _stream()),
+          "dpp_logdet_score")
+    return out
+
+
+def dpp_zscore(logdet: torch.Tensor):
+    """(mean, sd) as a (2,) tensor and z-scores — data_gen.py:406-408."""
+    lib = _lib.load()
+    _cu(logdet, torch.float64, "logdet")
+    N = logdet.numel()
+    stats = torch.empty(2, dtype=torch.float64, device=logdet.device)
+    z = torch.empty_like(logdet)
+    wsb = lib.b200bo_dpp_stats_workspace_bytes(N)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=logdet.device)
+    check(lib.b200bo_dpp_zscore(_ptr(logdet), N, _ptr(stats), _ptr(z), _ptr(ws), wsb, _stream()), "dpp_zscore")
+    return stats, z
+
+
+# ------------------------------------------------------------------ K-E
+
+def wildcat_surface(hseed: torch.Tensor, vecs: torch.Tensor, peak_xy: torch.Tensor, smooth: torch.Tensor,
+                    rug_amp: torch.Tensor) -> torch.Tensor:
+    """(S,101,101) f32 surfaces; hseed (S,) int64 (bit pattern of the uint64 hash), vecs (S,4,2) int8,
+    peak_xy (S,2) f64, smooth / rug_amp (S,) f64."""
+    lib = _lib.load()
+    _cu(hseed, torch.int64, "hseed")
+    _cu(vecs, torch.int8, "vecs")
+    _cu(peak_xy, torch.float64, "peak_xy")
+    _cu(smooth, torch.float64, "smooth")
+    _cu(rug_amp, torch.float64, "rug_amp")
+    S = hseed.numel()
+    if vecs.shape != (S, 4, 2) or peak_xy.shape != (S, 2) or smooth.numel() != S or rug_amp.numel() != S:
+        raise _lib.B200boError("wildcat_surface: inconsistent shapes")
+    surf = torch.empty((S, 101, 101), dtype=torch.float32, device=hseed.device)
+    check(lib.b200bo_wildcat_surface(_ptr(hseed), _ptr(vecs), _ptr(peak_xy), _ptr(smooth), _ptr(rug_amp), _ptr(surf), S,
+                                     _stream()), "wildcat_surface")
+    return surf
+
+
+def simplex_noise(hseed: int, vecs, xy: torch.Tensor) -> torch.Tensor:
+    """Raw 2-D simplex noise at xy (M,2) f64 for SimplexNoise(seed,2) with hashed seed / table given."""
+    import ctypes
+    lib = _lib.load()
+    _cu(xy, torch.float64, "xy")
+    M = xy.shape[0]
+    out = torch.empty(M, dtype=torch.float64, device=xy.device)
+    flat = [int(v) for row in vecs for v in row]
+    arr = (ctypes.c_int8 * 8)(*flat)
+    check(lib.b200bo_simplex_noise(int(hseed), ctypes.cast(arr, ctypes.c_void_p), _ptr(xy), _ptr(out), M, _stream()),
+          "simplex_noise")
+    return out
+
+
+# ------------------------------------------------------------------ K-A / K-C
+
+def wfrag_doubles(n_max: int) -> int:
+    return int(_lib.load().b200bo_wfrag_doubles(int(n_max)))
+
+
+def gp_assemble_chol(X, y, n, theta, kernel_id, want=("alpha", "wfrag"), status=None):
+    """K-A. X (T,n_max,2) f64, y (T,n_max) f64, n (T,) int32, theta (T,4) f64.
+    ``want`` selects outputs among L, Linv, alpha, logdet, wfrag. Returns dict (+ status)."""
+    lib = _lib.load()
+    _cu(X, torch.float64, "X"); _cu(y, torch.float64, "y"); _cu(n, torch.int32, "n"); _cu(theta, torch.float64, "theta")
+    T, n_max = y.shape
+    if X.shape != (T, n_max, 2) or n.shape != (T,) or theta.shape != (T, 4):
+        raise _lib.B200boError("gp_assemble_chol: inconsistent shapes")
+    dev = X.device
+    out = {}
+    if "L" in want: out["L"] = torch.empty((T, n_max, n_max), dtype=torch.float64, device=dev)
+    if "Linv" in want: out["Linv"] = torch.empty((T, n_max, n_max), dtype=torch.float64, device=dev)
+    if "alpha" in want: out["alpha"] = torch.empty((T, n_max), dtype=torch.float64, device=dev)
+    if "logdet" in want: out["logdet"] = torch.empty((T,), dtype=torch.float64, device=dev)
+    if "wfrag" in want: out["wfrag"] = torch.empty((T, wfrag_doubles(n_max)), dtype=torch.float64, device=dev)
+    if status is None:
+        status = torch.zeros(T, dtype=torch.int32, device=dev)
+    check(lib.b200bo_gp_assemble_chol(_ptr(X), _ptr(y), _ptr(n), _ptr(theta), _ptr(out.get("L")), _ptr(out.get("Linv")),
+                                      _ptr(out.get("alpha")), _ptr(out.get("logdet")), _ptr(out.get("wfrag")),
+                                      _ptr(status), T, n_max, int(kernel_id), _stream()), "gp_assemble_chol")
+    out["status"] = status
+    return out
+
+
+def gp_assemble_chol_into(X, y, n, theta, kernel_id, alpha, wfrag, status):
+    """Allocation-free K-A for the engine loop (alpha / wfrag / status preallocated)."""
+    lib = _lib.load()
+    T, n_max = y.shape
+    check(lib.b200bo_gp_assemble_chol(_ptr(X), _ptr(y), _ptr(n), _ptr(theta), None, None, _ptr(alpha), None, _ptr(wfrag),
+                                      _ptr(status), T, n_max, int(kernel_id), _stream()), "gp_assemble_chol")
+
+
+def mll_value_grad(X, y, n, raw, kernel_id, status=None):
+    """K-C. raw (T,4) f64 = (noise, c, raw_outputscale, raw_lengthscale) -> value (T,), grad (T,4), status."""
+    lib = _lib.load()
+    _cu(X, torch.float64, "X"); _cu(y, torch.float64, "y"); _cu(n, torch.int32, "n"); _cu(raw, torch.float64, "raw")
+    T, n_max = y.shape
+    dev = X.device
+    value = torch.empty(T, dtype=torch.float64, device=dev)
+    grad = torch.empty((T, 4), dtype=torch.float64, device=dev)
+    if status is None:
+        status = torch.zeros(T, dtype=torch.int32, device=dev)
+    check(lib.b200bo_mll_value_grad(_ptr(X), _ptr(y), _ptr(n), _ptr(raw), _ptr(value), _ptr(grad), _ptr(status), T, n_max,
+                                    int(kernel_id), _stream()), "mll_value_grad")
+    return value, grad, status
+
+
+# ------------------------------------------------------------------ K-B
+
+def grid_acq_workspace(T: int, G: int, device) -> torch.Tensor:
+    nbytes = int(_lib.load().b200bo_grid_acq_workspace_bytes(int(T), int(G)))
+    return torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
+
+
+def grid_posterior_acq_argmax(grid, X, wfrag, alpha, n, theta, best_f, kernel_id, acq_id=EI, acq_param=0.0,
+                              var_floor=VAR_FLOOR, mask_observed=True, extra_mask=None, debug=False, status=None,
+                              ws=None, arg_idx=None, arg_val=None):
+    """K-B. Returns dict(idx (T,) int32, val (T,) f64, status[, mu, var, acq (T,G)])."""
+    lib = _lib.load()
+    _cu(grid, torch.float64, "grid"); _cu(X, torch.float64, "X"); _cu(wfrag, torch.float64, "wfrag")
+    _cu(alpha, torch.float64, "alpha"); _cu(n, torch.int32, "n"); _cu(theta, torch.float64, "theta")
+    _cu(best_f, torch.float64, "best_f")
+    G = grid.shape[0]
+    T, n_max = alpha.shape
+    dev = grid.device
+    if extra_mask is not None:
+        _cu(extra_mask, torch.uint8, "extra_mask")
+    if wfrag.shape != (T, wfrag_doubles(n_max)):
+        raise _lib.B200boError("grid_posterior_acq_argmax: wfrag has the wrong shape for n_max")
+    if arg_idx is None: arg_idx = torch.empty(T, dtype=torch.int32, device=dev)
+    if arg_val is None: arg_val = torch.empty(T, dtype=torch.float64, device=dev)
+    if status is None: status = torch.zeros(T, dtype=torch.int32, device=dev)
+    if ws is None: ws = grid_acq_workspace(T, G, dev)
+    mu = var = acq = None
+    if debug:
+        mu = torch.empty((T, G), dtype=torch.float64, device=dev)
+        var = torch.empty_like(mu)
+        acq = torch.empty_like(mu)
+    check(lib.b200bo_grid_posterior_acq_argmax(
+        _ptr(grid), G, _ptr(X), _ptr(wfrag), _ptr(alpha), _ptr(n), _ptr(theta), _ptr(best_f), _ptr(extra_mask),
+        1 if mask_observed else 0, int(acq_id), float(acq_param), float(var_floor), _ptr(arg_idx), _ptr(arg_val),
+        _ptr(mu), _ptr(var), _ptr(acq), _ptr(status), T, n_max, int(kernel_id), _ptr(ws), ws.numel(), _stream()),
+        "grid_posterior_acq_argmax")
+    out = dict(idx=arg_idx, val=arg_val, status=status)
+    if debug:
+        out.update(mu=mu, var=var, acq=acq)
+    return out

@@ -1,0 +1,247 @@
+// K-D: ranked-DPP set scoring — log det exp(-gamma * D) for N index sets.
+//
+// Replaces diverse_data_generator.twoD_score (Src/data_gen.py:484-497) looped over the
+// superset (data_gen.py:403) and the mean / np.std / z-score block (data_gen.py:406-408).
+//
+// Roofline: FP64-pipe bound. Per set (k = 10): 45 pair kernels (sub, sub, mul, fma, sqrt,
+// mul, mul, exp) + a 10x10 Cholesky (220 FMA, 10 sqrt, 45 div-equivalents) + 10 log;
+// HBM traffic is 4k bytes in + 8 bytes out = 48 B per set, pool (160 KB) stays in L1/L2.
+//
+// k <= KREG_MAX: one set per thread, packed lower triangle held in registers (fully
+// unrolled, no pivoting: S is symmetric positive definite in exact arithmetic).
+// larger k: one set per CTA, matrix in shared memory.
+#include "common.cuh"
+
+namespace b200bo {
+
+constexpr int KREG_MAX = 12;
+
+// D = (sqrt(dx^2 + dy^2))^2 : scipy pdist('euclidean') then **2 (data_gen.py:489).
+__device__ __forceinline__ double dpp_entry(double ax, double ay, double bx, double by, double neg_gamma) {
+  double dx = ax - bx, dy = ay - by;
+  double d = sqrt(dx * dx + dy * dy);
+  return exp(neg_gamma * (d * d));
+}
+
+template <int K>
+__global__ void __launch_bounds__(128)
+dpp_logdet_reg_kernel(const double2* __restrict__ pool, const int32_t* __restrict__ idx, long long N, double neg_gamma,
+                      double* __restrict__ out) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double px[K], py[K];
+  const int32_t* row = idx + i * K;
+#pragma unroll
+  for (int a = 0; a < K; ++a) {
+    double2 p = __ldg(&pool[row[a]]);
+    px[a] = p.x;
+    py[a] = p.y;
+  }
+  // packed lower triangle, A[r][c] (c <= r) at r*(r+1)/2 + c
+  double A[K * (K + 1) / 2];
+#pragma unroll
+  for (int r = 0; r < K; ++r) {
+#pragma unroll
+    for (int c = 0; c < r; ++c) A[r * (r + 1) / 2 + c] = dpp_entry(px[r], py[r], px[c], py[c], neg_gamma);
+    A[r * (r + 1) / 2 + r] = 1.0;   // exp(-gamma * 0)
+  }
+  double acc = 0.0;
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    double d = A[j * (j + 1) / 2 + j];
+    ok = ok && (d > 0.0);
+    acc += log(d);
+    double inv = 1.0 / sqrt(d);
+#pragma unroll
+    for (int r = j + 1; r < K; ++r) A[r * (r + 1) / 2 + j] *= inv;
+#pragma unroll
+    for (int c = j + 1; c < K; ++c) {
+      double lcj = A[c * (c + 1) / 2 + j];
+#pragma unroll
+      for (int r = c; r < K; ++r) A[r * (r + 1) / 2 + c] = fma(-A[r * (r + 1) / 2 + j], lcj, A[r * (r + 1) / 2 + c]);
+    }
+  }
+  out[i] = ok ? acc : nan("");
+}
+
+// generic k: one set per CTA, full matrix in shared memory (k*k doubles).
+__global__ void __launch_bounds__(128)
+dpp_logdet_smem_kernel(const double2* __restrict__ pool, const int32_t* __restrict__ idx, long long N, int k,
+                       double neg_gamma, double* __restrict__ out) {
+  extern __shared__ double sm[];
+  double* A = sm;                 // k*k, row-major, lower part used
+  double* px = sm + (size_t)k * k;
+  double* py = px + k;
+  __shared__ double s_acc;
+  __shared__ int s_ok;
+  for (long long set = blockIdx.x; set < N; set += gridDim.x) {
+    const int32_t* row = idx + set * k;
+    for (int a = threadIdx.x; a < k; a += blockDim.x) {
+      double2 p = __ldg(&pool[row[a]]);
+      px[a] = p.x;
+      py[a] = p.y;
+    }
+    if (threadIdx.x == 0) { s_acc = 0.0; s_ok = 1; }
+    __syncthreads();
+    for (int e = threadIdx.x; e < k * k; e += blockDim.x) {
+      int r = e / k, c = e - r * k;
+      if (c <= r) A[e] = (c == r) ? 1.0 : dpp_entry(px[r], py[r], px[c], py[c], neg_gamma);
+    }
+    __syncthreads();
+    for (int j = 0; j < k; ++j) {
+      double d = A[j * k + j];
+      __syncthreads();   // everyone has read the pivot before column j is scaled
+      if (threadIdx.x == 0) {
+        if (!(d > 0.0)) s_ok = 0;
+        s_acc += log(d);
+      }
+      double inv = 1.0 / sqrt(d);
+      for (int r = j + 1 + threadIdx.x; r < k; r += blockDim.x) A[r * k + j] *= inv;
+      __syncthreads();
+      // trailing update of the lower triangle: rows r > j, cols j < c <= r
+      int m = k - j - 1;
+      for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+        int rr = e / m, cc = e - rr * m;
+        if (cc <= rr) {
+          int r = j + 1 + rr, c = j + 1 + cc;
+          A[r * k + c] = fma(-A[r * k + j], A[c * k + j], A[r * k + c]);
+        }
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[set] = s_ok ? s_acc : nan("");
+    __syncthreads();
+  }
+}
+
+// ---- statistics: mean, population sd (np.std, ddof 0), z = (x - mean) / sd -----------
+// two-pass (mean, then centred sum of squares) like numpy; deterministic tree order:
+// per-block partials in ws, final reduction by one block.
+__global__ void __launch_bounds__(256) reduce_sum_kernel(const double* __restrict__ x, long long N, double shift,
+                                                         int square, double* __restrict__ partial) {
+  __shared__ double sh[8];
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+    double v = x[i] - shift;
+    acc += square ? v * v : v;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < 8 ? sh[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+  }
+}
+
+// stage 0: stats[0] = sum(partial)/N ; stage 1: stats[1] = sqrt(sum(partial)/N)
+__global__ void __launch_bounds__(256) finish_stat_kernel(const double* __restrict__ partial, int nblocks, long long N,
+                                                          int stage, double* __restrict__ stats) {
+  __shared__ double sh[8];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) acc += partial[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    if (stage == 0) stats[0] = t / (double)N;
+    else stats[1] = sqrt(t / (double)N);
+  }
+}
+
+__global__ void __launch_bounds__(256) centred_sq_kernel(const double* __restrict__ x, long long N,
+                                                         const double* __restrict__ stats, double* __restrict__ partial) {
+  __shared__ double sh[8];
+  double mean = stats[0];
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+    double v = x[i] - mean;
+    acc = fma(v, v, acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < 8 ? sh[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) zscore_kernel(const double* __restrict__ x, long long N,
+                                                     const double* __restrict__ stats, double* __restrict__ z) {
+  double mean = stats[0], sd = stats[1];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
+    z[i] = (x[i] - mean) / sd;
+}
+
+constexpr int STAT_BLOCKS = 592;   // 4 x 148 SMs
+
+template <int K>
+static void launch_reg(const double* pool, const int32_t* idx, long long N, double gamma, double* out, cudaStream_t st) {
+  int threads = 128;
+  long long blocks = (N + threads - 1) / threads;
+  dpp_logdet_reg_kernel<K><<<(unsigned)blocks, threads, 0, st>>>(reinterpret_cast<const double2*>(pool), idx, N, -gamma, out);
+}
+
+}  // namespace b200bo
+
+extern "C" {
+
+int b200bo_dpp_logdet_score(const double* pool, int pool_size, const int32_t* idx, long long N, int k, double gamma,
+                            double* logdet, void* stream) {
+  using namespace b200bo;
+  if (!pool || !idx || !logdet) return arg_error("dpp_logdet_score: null pointer");
+  if (pool_size <= 0 || k < 1 || N < 0) return arg_error("dpp_logdet_score: bad sizes pool=%d k=%d N=%lld", pool_size, k, N);
+  if (k > 160) return arg_error("dpp_logdet_score: k=%d > 160 unsupported", k);
+  if (N == 0) return 0;
+  if (N > 2147483647LL * 128) return arg_error("dpp_logdet_score: N too large");
+  cudaStream_t st = as_stream(stream);
+  switch (k) {
+    case 1: launch_reg<1>(pool, idx, N, gamma, logdet, st); break;
+    case 2: launch_reg<2>(pool, idx, N, gamma, logdet, st); break;
+    case 3: launch_reg<3>(pool, idx, N, gamma, logdet, st); break;
+    case 4: launch_reg<4>(pool, idx, N, gamma, logdet, st); break;
+    case 5: launch_reg<5>(pool, idx, N, gamma, logdet, st); break;
+    case 6: launch_reg<6>(pool, idx, N, gamma, logdet, st); break;
+    case 7: launch_reg<7>(pool, idx, N, gamma, logdet, st); break;
+    case 8: launch_reg<8>(pool, idx, N, gamma, logdet, st); break;
+    case 9: launch_reg<9>(pool, idx, N, gamma, logdet, st); break;
+    case 10: launch_reg<10>(pool, idx, N, gamma, logdet, st); break;
+    case 11: launch_reg<11>(pool, idx, N, gamma, logdet, st); break;
+    case 12: launch_reg<12>(pool, idx, N, gamma, logdet, st); break;
+    default: {
+      size_t smem = ((size_t)k * k + 2 * (size_t)k) * sizeof(double);
+      cudaError_t e = cudaFuncSetAttribute(dpp_logdet_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_status(e, "dpp_logdet_score: smem attribute");
+      long long blocks = N < 148 * 8 ? N : 148 * 8;
+      dpp_logdet_smem_kernel<<<(unsigned)blocks, 128, smem, st>>>(reinterpret_cast<const double2*>(pool), idx, N, k, -gamma, logdet);
+    }
+  }
+  B200BO_CHECK_LAUNCH("dpp_logdet_score");
+  return 0;
+}
+
+size_t b200bo_dpp_stats_workspace_bytes(long long N) { (void)N; return b200bo::STAT_BLOCKS * sizeof(double); }
+
+int b200bo_dpp_zscore(const double* logdet, long long N, double* stats, double* z, void* ws, size_t ws_bytes, void* stream) {
+  using namespace b200bo;
+  if (!logdet || !stats || !ws) return arg_error("dpp_zscore: null pointer");
+  if (N <= 0) return arg_error("dpp_zscore: N=%lld", N);
+  if (ws_bytes < b200bo_dpp_stats_workspace_bytes(N)) return arg_error("dpp_zscore: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  double* partial = reinterpret_cast<double*>(ws);
+  reduce_sum_kernel<<<STAT_BLOCKS, 256, 0, st>>>(logdet, N, 0.0, 0, partial);
+  finish_stat_kernel<<<1, 256, 0, st>>>(partial, STAT_BLOCKS, N, 0, stats);
+  centred_sq_kernel<<<STAT_BLOCKS, 256, 0, st>>>(logdet, N, stats, partial);
+  finish_stat_kernel<<<1, 256, 0, st>>>(partial, STAT_BLOCKS, N, 1, stats);
+  if (z) zscore_kernel<<<STAT_BLOCKS, 256, 0, st>>>(logdet, N, stats, z);
+  B200BO_CHECK_LAUNCH("dpp_zscore");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,323 @@
+// K-B: fused grid posterior + acquisition + arg-max (the roofline kernel of this repo).
+//
+// Replaces ExpectedImprovement(model, best_f) -> SingleTaskGP.posterior and the continuous
+// optimize_acqf of the reference (Src/BO.py:158-161, 72-83) by a dense
+// evaluation + arg-max over the candidate grid. For trial t and candidate x:
+//     k*_j = s k(|x - x_j| / l),  mu = c + k*^T alpha,  var = s - | L^-1 k* |^2,
+//     acq  = EI / UCB / PI (mu, max(var, var_floor), best_f)
+// Nothing of size n x G ever exists in HBM: the cross-covariance tile lives in the
+// B-fragment registers of mma.sync.m8n8k4.f64 (DMMA), L^-1 (lower triangular, fragment-major)
+// is staged once per CTA in shared memory, and only (value, index) pairs leave the SM.
+//
+// Mapping: one CTA = one (trial, column chunk); a warp walks 32-column super-tiles as four
+// 8-column MMA tiles. For tile rows I (8 rows) only k-blocks J <= 2I+1 (lower triangle) are
+// issued. Each lane evaluates the kernel for exactly the (j, column) pairs its B fragment
+// needs, so there is no redundancy and no shared-memory staging of k*.
+//
+// Roofline: FP64 pipe (DMMA and DFMA share it on B200: tools/microbench/fp64_peaks.cu).
+// Algorithmic flops per (trial, launch): F_B(n, G) = G (n^2 + 17 n + 30);
+// algorithmic bytes: 24 n + 8 wfrag_doubles(n) + 40 read, 16 written per CTA + 16 G grid
+// bytes (L2-resident, shared by all trials).
+#include "common.cuh"
+#include <limits.h>
+
+namespace b200bo {
+
+constexpr int GA_THREADS = 256;
+constexpr int GA_WARPS = GA_THREADS / 32;
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+struct GridAcqParams {
+  const double2* grid;      // (G) candidates
+  int G;
+  const double* X;          // (T, n_max, 2)
+  const double* wfrag;      // (T, wstride)
+  const double* alpha;      // (T, n_max)
+  const int32_t* n;         // (T)
+  const double* theta;      // (T, 4)
+  const double* best_f;     // (T)
+  const uint8_t* extra_mask;  // (G) or null
+  int mask_observed;
+  int acq_id;
+  double acq_param;         // UCB: sqrt(beta)
+  double var_floor;
+  double* part_val;         // (T, chunks)
+  int32_t* part_idx;        // (T, chunks)
+  double* mu_out;           // (T, G) or null
+  double* var_out;
+  double* acq_out;
+  int32_t* status;          // (T)
+  int n_max;
+  size_t wstride;
+  int chunks;
+  int cols_per_cta;         // multiple of 32
+};
+
+template <int KID, int NI_MAX>
+__global__ void __launch_bounds__(GA_THREADS, (NI_MAX <= 8 ? 2 : 1))
+grid_acq_kernel(const GridAcqParams p) {
+  extern __shared__ double sm[];
+  const int t = blockIdx.x / p.chunks;
+  const int chunk = blockIdx.x - t * p.chunks;
+  const int n = p.n[t];
+  if (n <= 0) return;                     // finished / inactive trial (uniform per CTA)
+  const int nI = (n + 7) >> 3;
+  const int nJ = 2 * nI;
+  const int npad = 8 * nI;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nblk = nI * (nI + 1);
+
+  double* wsm = sm;                       // nblk * 32
+  double* xs = sm + (size_t)nblk * 32;    // npad
+  double* ys = xs + npad;
+  double* al = ys + npad;
+  __shared__ double red_val[GA_WARPS];
+  __shared__ int red_idx[GA_WARPS];
+  __shared__ int red_flag;
+
+  {   // stage L^-1 fragments (contiguous prefix of the trial's wfrag) and the observations
+    const double2* src = reinterpret_cast<const double2*>(p.wfrag + (size_t)t * p.wstride);
+    double2* dst = reinterpret_cast<double2*>(wsm);
+    for (int e = threadIdx.x; e < nblk * 16; e += GA_THREADS) dst[e] = src[e];
+    for (int j = threadIdx.x; j < npad; j += GA_THREADS) {
+      bool v = j < n;
+      xs[j] = v ? p.X[((size_t)t * p.n_max + j) * 2] : 0.0;
+      ys[j] = v ? p.X[((size_t)t * p.n_max + j) * 2 + 1] : 0.0;
+      al[j] = v ? p.alpha[(size_t)t * p.n_max + j] : 0.0;
+    }
+    if (threadIdx.x == 0) red_flag = 0;
+  }
+  const double cst = p.theta[(size_t)t * 4 + 1];
+  const double sc = p.theta[(size_t)t * 4 + 2];
+  const double ell = p.theta[(size_t)t * 4 + 3];
+  const KernParams kp = make_kern_params(sc, ell, KID);
+  const double best_f = p.best_f[t];
+  __syncthreads();
+
+  const int col0 = chunk * p.cols_per_cta;
+  const int col_end = min(p.G, col0 + p.cols_per_cta);
+  const int jrow = lane & 3;        // k-row inside a 4-block / C column pair
+  const int bcol = lane >> 2;       // B column / C row
+
+  double best_v = -INFINITY;
+  int best_i = INT_MAX;
+  int flags = 0;
+
+  for (int base = col0 + warp * 32; base < col_end; base += GA_WARPS * 32) {
+    double my_ss = 0.0, my_mu = 0.0;
+    int my_masked = 0;
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+      const int gb = min(base + 8 * q + bcol, p.G - 1);
+      const double2 gp = __ldg(&p.grid[gb]);
+      double kval[2 * NI_MAX];
+      double mu_part = 0.0;
+      int masked = 0;
+#pragma unroll
+      for (int J = 0; J < 2 * NI_MAX; ++J) {
+        kval[J] = 0.0;
+        if (J < nJ) {
+          const int j = 4 * J + jrow;
+          const double dx = gp.x - xs[j], dy = gp.y - ys[j];
+          const double r2 = dx * dx + dy * dy;
+          double kv = kernel_from_r2<KID>(r2, sc, ell, kp.a_scale);
+          const bool valid = j < n;
+          kv = valid ? kv : 0.0;
+          masked |= (valid && r2 == 0.0) ? 1 : 0;
+          kval[J] = kv;
+          mu_part = fma(kv, al[j], mu_part);
+        }
+      }
+      // V = L^-1 K* on the FP64 MMA path; accumulate squared entries per C column
+      double ss0 = 0.0, ss1 = 0.0;
+#pragma unroll
+      for (int I = 0; I < NI_MAX; ++I) {
+        if (I < nI) {
+          double c0 = 0.0, c1 = 0.0;
+          const double* wrow = wsm + (size_t)(I * (I + 1)) * 32 + lane;
+#pragma unroll
+          for (int J = 0; J <= 2 * I + 1; ++J) dmma_m8n8k4(c0, c1, wrow[J * 32], kval[J]);
+          ss0 = fma(c0, c0, ss0);
+          ss1 = fma(c1, c1, ss1);
+        }
+      }
+      // rows live in lane>>2: reduce over xor 4, 8, 16
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        ss0 += __shfl_xor_sync(0xffffffffu, ss0, o);
+        ss1 += __shfl_xor_sync(0xffffffffu, ss1, o);
+      }
+      // k-rows live in lane&3: reduce over xor 1, 2
+#pragma unroll
+      for (int o = 1; o < 4; o <<= 1) {
+        mu_part += __shfl_xor_sync(0xffffffffu, mu_part, o);
+        masked |= __shfl_xor_sync(0xffffffffu, masked, o);
+      }
+      // hand column cc = lane&7 of this tile to lane 8q + cc
+      const int cc = lane & 7;
+      const double t0 = __shfl_sync(0xffffffffu, ss0, cc >> 1);
+      const double t1 = __shfl_sync(0xffffffffu, ss1, cc >> 1);
+      const double tm = __shfl_sync(0xffffffffu, mu_part, cc * 4);
+      const int tk = __shfl_sync(0xffffffffu, masked, cc * 4);
+      if ((lane >> 3) == q) {
+        my_ss = (cc & 1) ? t1 : t0;
+        my_mu = tm;
+        my_masked = tk;
+      }
+    }
+    const int g = base + lane;
+    if (g < col_end) {
+      const double mu = cst + my_mu;
+      const double var = sc - my_ss;
+      double a;
+      if (p.acq_id == B200BO_ACQ_UCB) a = acquisition<B200BO_ACQ_UCB>(mu, var, best_f, p.acq_param, p.var_floor);
+      else if (p.acq_id == B200BO_ACQ_PI) a = acquisition<B200BO_ACQ_PI>(mu, var, best_f, p.acq_param, p.var_floor);
+      else a = acquisition<B200BO_ACQ_EI>(mu, var, best_f, p.acq_param, p.var_floor);
+      if (p.mu_out) p.mu_out[(size_t)t * p.G + g] = mu;
+      if (p.var_out) p.var_out[(size_t)t * p.G + g] = var;
+      if (p.acq_out) p.acq_out[(size_t)t * p.G + g] = a;
+      bool m = (p.mask_observed && my_masked) || (p.extra_mask && p.extra_mask[g]);
+      if (!m) {
+        if (isnan(a) || a == INFINITY) flags |= B200BO_ST_NONFINITE;
+        if (!isnan(a) && better(a, g, best_v, best_i)) { best_v = a; best_i = g; }
+      }
+    }
+  }
+  warp_argmax(best_v, best_i);
+  flags = __reduce_or_sync(0xffffffffu, flags);
+  if (lane == 0) {
+    red_val[warp] = best_v;
+    red_idx[warp] = best_i;
+    if (flags) atomicOr(&red_flag, flags);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double bv = red_val[0];
+    int bi = red_idx[0];
+    for (int w = 1; w < GA_WARPS; ++w)
+      if (better(red_val[w], red_idx[w], bv, bi)) { bv = red_val[w]; bi = red_idx[w]; }
+    p.part_val[(size_t)t * p.chunks + chunk] = bv;
+    p.part_idx[(size_t)t * p.chunks + chunk] = bi;
+    if (red_flag && p.status) atomicOr(&p.status[t], red_flag);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+argmax_finish_kernel(const double* __restrict__ part_val, const int32_t* __restrict__ part_idx, int chunks, int T,
+                     const int32_t* __restrict__ n, int32_t* __restrict__ arg_idx, double* __restrict__ arg_val,
+                     int32_t* __restrict__ status) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  if (n[t] <= 0) {                         // inactive trial: nothing was evaluated
+    arg_idx[t] = -1;
+    if (arg_val) arg_val[t] = -INFINITY;
+    return;
+  }
+  double bv = -INFINITY;
+  int bi = INT_MAX;
+  for (int c = 0; c < chunks; ++c) {
+    double v = part_val[(size_t)t * chunks + c];
+    int i = part_idx[(size_t)t * chunks + c];
+    if (better(v, i, bv, bi)) { bv = v; bi = i; }
+  }
+  if (bi == INT_MAX) {
+    bi = -1;
+    if (status) atomicOr(&status[t], B200BO_ST_ALL_MASKED);
+  }
+  arg_idx[t] = bi;
+  if (arg_val) arg_val[t] = bv;
+}
+
+inline int pick_chunks(int T, int G) {
+  int max_chunks = (G + 255) / 256;
+  int want = (4 * 148 + T - 1) / T;
+  if (want < 1) want = 1;
+  return want > max_chunks ? max_chunks : want;
+}
+
+template <int KID, int NI_MAX>
+static int launch_grid_acq(const GridAcqParams& p, int T, cudaStream_t st) {
+  const int nI = NI_MAX;
+  size_t smem = ((size_t)nI * (nI + 1) * 32 + 3 * 8 * (size_t)nI) * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(grid_acq_kernel<KID, NI_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_status(e, "grid_posterior_acq_argmax: smem attribute");
+  // dynamic smem sized by the largest n actually possible in this instantiation would waste
+  // occupancy for small n; size it by n_max rounded to the tile instead.
+  int nIa = (p.n_max + 7) / 8;
+  if (nIa > NI_MAX) nIa = NI_MAX;
+  smem = ((size_t)nIa * (nIa + 1) * 32 + 3 * 8 * (size_t)nIa) * sizeof(double);
+  grid_acq_kernel<KID, NI_MAX><<<(unsigned)((size_t)T * p.chunks), GA_THREADS, smem, st>>>(p);
+  return 0;
+}
+
+template <int KID>
+static int dispatch_ni(const GridAcqParams& p, int T, cudaStream_t st) {
+  if (p.n_max <= 32) return launch_grid_acq<KID, 4>(p, T, st);
+  if (p.n_max <= 64) return launch_grid_acq<KID, 8>(p, T, st);
+  return launch_grid_acq<KID, 16>(p, T, st);
+}
+
+}  // namespace b200bo
+
+extern "C" {
+
+size_t b200bo_grid_acq_workspace_bytes(int T, int G) {
+  if (T <= 0 || G <= 0) return 0;
+  int chunks = b200bo::pick_chunks(T, G);
+  return (size_t)T * chunks * (sizeof(double) + sizeof(int32_t)) + 16;
+}
+
+int b200bo_grid_posterior_acq_argmax(const double* grid, int G, const double* X, const double* wfrag,
+                                     const double* alpha, const int32_t* n, const double* theta,
+                                     const double* best_f, const uint8_t* extra_mask, int mask_observed, int acq_id,
+                                     double acq_param, double var_floor, int32_t* arg_idx, double* arg_val, double* mu,
+                                     double* var, double* acq, int32_t* status, int T, int n_max, int kernel_id,
+                                     void* ws, size_t ws_bytes, void* stream) {
+  using namespace b200bo;
+  if (!grid || !X || !wfrag || !alpha || !n || !theta || !best_f || !arg_idx || !ws)
+    return arg_error("grid_posterior_acq_argmax: null pointer");
+  if (T < 0 || G < 1 || n_max < 1 || n_max > B200BO_NMAX)
+    return arg_error("grid_posterior_acq_argmax: T=%d G=%d n_max=%d (max %d)", T, G, n_max, B200BO_NMAX);
+  if (kernel_id < 0 || kernel_id > 3) return arg_error("grid_posterior_acq_argmax: kernel_id=%d", kernel_id);
+  if (acq_id < 0 || acq_id > 2) return arg_error("grid_posterior_acq_argmax: acq_id=%d", acq_id);
+  if (acq_id == B200BO_ACQ_UCB && !(acq_param >= 0.0)) return arg_error("grid_posterior_acq_argmax: UCB beta < 0");
+  if (ws_bytes < b200bo_grid_acq_workspace_bytes(T, G)) return arg_error("grid_posterior_acq_argmax: workspace too small");
+  if (T == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  GridAcqParams p;
+  p.grid = reinterpret_cast<const double2*>(grid);
+  p.G = G;
+  p.X = X; p.wfrag = wfrag; p.alpha = alpha; p.n = n; p.theta = theta; p.best_f = best_f;
+  p.extra_mask = extra_mask;
+  p.mask_observed = mask_observed;
+  p.acq_id = acq_id;
+  p.acq_param = acq_id == B200BO_ACQ_UCB ? sqrt(acq_param) : acq_param;
+  p.var_floor = var_floor;
+  p.chunks = pick_chunks(T, G);
+  p.cols_per_cta = (((G + p.chunks - 1) / p.chunks + 255) / 256) * 256;
+  p.part_val = reinterpret_cast<double*>(ws);
+  p.part_idx = reinterpret_cast<int32_t*>(p.part_val + (size_t)T * p.chunks);
+  p.mu_out = mu; p.var_out = var; p.acq_out = acq;
+  p.status = status;
+  p.n_max = n_max;
+  p.wstride = b200bo_wfrag_doubles(n_max);
+  int rc;
+  switch (kernel_id) {
+    case B200BO_KERNEL_RBF: rc = dispatch_ni<B200BO_KERNEL_RBF>(p, T, st); break;
+    case B200BO_KERNEL_MATERN12: rc = dispatch_ni<B200BO_KERNEL_MATERN12>(p, T, st); break;
+    case B200BO_KERNEL_MATERN32: rc = dispatch_ni<B200BO_KERNEL_MATERN32>(p, T, st); break;
+    default: rc = dispatch_ni<B200BO_KERNEL_MATERN52>(p, T, st); break;
+  }
+  if (rc) return rc;
+  B200BO_CHECK_LAUNCH("grid_posterior_acq_argmax");
+  argmax_finish_kernel<<<(T + 127) / 128, 128, 0, st>>>(p.part_val, p.part_idx, p.chunks, T, n, arg_idx, arg_val, status);
+  B200BO_CHECK_LAUNCH("grid_posterior_acq_argmax: finish");
+  return 0;
+}
+
+}  // extern "C"

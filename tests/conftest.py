@@ -1,0 +1,60 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "jmd-diversity-in-bayesian-optimization_b200")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def golden():
+    cache = {}
+
+    def load(name):
+        if name not in cache:
+            path = os.path.join(GOLDEN, name)
+            if name.endswith(".npz"):
+                cache[name] = dict(np.load(path, allow_pickle=False))
+            else:
+                import json
+                with open(path) as fh:
+                    cache[name] = json.load(fh)
+        return cache[name]
+
+    return load
+
+
+@pytest.fixture(scope="session")
+def lattice_grid():
+    """data_gen.constructX(): (10000,2) f64 integer lattice on [0,99]^2, x fastest."""
+    ax = np.arange(0, 100, 1.0)
+    return np.stack(np.meshgrid(ax, ax), axis=-1).reshape(-1, 2).astype(np.float64)
+
+
+AUTHOR_THETA_RAW = (0.0017619397258386016, 41.82688735961914, 190.43237411499024, 9.869425163269042)
+"""(raw_noise, constant, raw_outputscale, raw_lengthscale): dominant KDE modes of the authors' fits for
+smoothness 0.2 / ruggedness 0.2 (tests/golden/author_hyperparams.json; BOloop_fixparam uses [0], BO.py:395)."""

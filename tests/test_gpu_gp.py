@@ -1,0 +1,183 @@
+"""GPU parity: K-A (assemble + Cholesky + L^-1 + alpha), K-B (fused grid posterior + acquisition +
+arg-max) and K-C (marginal likelihood value and gradient) vs the fp64 oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import AUTHOR_THETA_RAW
+from oracle import gp as ogp
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _theta():
+    return ogp.raw_to_theta(AUTHOR_THETA_RAW)
+
+
+def _make_batch(golden, lattice_grid, T, n_list, n_max, seed=0, theta=None):
+    rng = np.random.default_rng(seed)
+    surf = golden("wildcat.npz")["surf_0"]
+    X = np.zeros((T, n_max, 2))
+    y = np.zeros((T, n_max))
+    n = np.zeros(T, dtype=np.int32)
+    th = np.zeros((T, 4))
+    for t in range(T):
+        nt = n_list[t % len(n_list)]
+        idx = rng.choice(10000, nt, replace=False)
+        X[t, :nt] = lattice_grid[idx]
+        y[t, :nt] = surf[:100, :100].reshape(-1)[idx]
+        n[t] = nt
+        th[t] = theta if theta is not None else _theta() * rng.uniform(0.7, 1.3, 4)
+    return X, y, n, th
+
+
+def _to(a, dtype=None):
+    return torch.as_tensor(np.ascontiguousarray(a), device=DEV) if dtype is None else torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device=DEV)
+
+
+@pytest.mark.parametrize("kid", [0, 1, 2, 3])
+def test_assemble_chol_alpha_linv(golden, lattice_grid, kid):
+    from b200bo import ops
+    n_max = 64
+    X, y, n, th = _make_batch(golden, lattice_grid, 12, [1, 2, 7, 10, 33, 64], n_max, seed=kid)
+    out = ops.gp_assemble_chol(_to(X), _to(y), _to(n), _to(th), kid, want=("L", "Linv", "alpha", "logdet", "wfrag"))
+    torch.cuda.synchronize()
+    for t in range(len(n)):
+        nt = n[t]
+        L, alpha, Linv, st = ogp.gp_state(X[t, :nt], y[t, :nt], th[t], kid)
+        assert out["status"][t].item() == st == 0
+        Lg = out["L"][t].cpu().numpy()
+        assert np.allclose(Lg[:nt, :nt], L, rtol=1e-9, atol=1e-12 * th[t, 2])
+        assert np.all(Lg[nt:] == 0) and np.all(np.triu(Lg, 1) == 0)
+        Wg = out["Linv"][t].cpu().numpy()
+        scale = np.abs(Linv).max()
+        assert np.allclose(Wg[:nt, :nt], Linv, rtol=1e-7, atol=1e-9 * scale)
+        ag = out["alpha"][t].cpu().numpy()
+        assert np.allclose(ag[:nt], alpha, rtol=1e-7, atol=1e-9 * np.abs(alpha).max())
+        assert np.all(ag[nt:] == 0)
+        ld = 2 * np.sum(np.log(np.diag(L)))
+        assert abs(out["logdet"][t].item() - ld) <= 1e-10 * abs(ld) + 1e-12
+        # fragment layout: block (I,J) at I(I+1)+J, lane l -> W[8I + l/4][4J + l%4]
+        wf = out["wfrag"][t].cpu().numpy()
+        nI = (n_max + 7) // 8
+        for I in range(nI):
+            for J in range(2 * I + 2):
+                blk = wf[(I * (I + 1) + J) * 32:(I * (I + 1) + J + 1) * 32]
+                for lane in (0, 5, 31):
+                    r, c = 8 * I + lane // 4, 4 * J + lane % 4
+                    assert blk[lane] == (Wg[r, c] if (r < n_max and c < n_max) else 0.0)
+
+
+def test_chol_jitter_and_failure(lattice_grid):
+    """Duplicate observations with ~zero noise make Khat singular: jitter path (status bit 0);
+    a negative 'noise' cannot be repaired: failure bit, NaN alpha, batch continues."""
+    from b200bo import ops
+    n_max = 8
+    X = np.zeros((3, n_max, 2)); y = np.zeros((3, n_max)); n = np.array([4, 4, 4], dtype=np.int32)
+    pts = np.array([[1.0, 1.0], [1.0, 1.0], [5.0, 9.0], [20.0, 3.0]])
+    X[:, :4] = pts
+    y[:, :4] = [1.0, 1.0, 2.0, 3.0]
+    th = np.array([[1e-3, 0.0, 1.0, 5.0], [0.0, 0.0, 1.0, 5.0], [-10.0, 0.0, 1.0, 5.0]])
+    out = ops.gp_assemble_chol(_to(X), _to(y), _to(n), _to(th), 3, want=("alpha", "L"))
+    st = out["status"].cpu().numpy()
+    for t in range(3):
+        _, alpha, _, st_o = ogp.gp_state(X[t, :4], y[t, :4], th[t], 3)
+        assert st[t] == st_o, (t, st[t], st_o)
+    assert st[0] == 0 and st[1] == ogp.ST_JITTER and st[2] == (ogp.ST_JITTER | ogp.ST_CHOL_FAIL)
+    assert np.all(np.isnan(out["alpha"][2, :4].cpu().numpy()))
+    assert np.all(np.isfinite(out["alpha"][1, :4].cpu().numpy()))
+
+
+@pytest.mark.parametrize("kid,acq", [(3, 0), (2, 0), (1, 0), (0, 0), (3, 1), (3, 2)])
+def test_grid_posterior_acq_argmax(golden, lattice_grid, kid, acq):
+    from b200bo import ops
+    n_max = 40
+    n_list = [1, 3, 10, 11, 17, 25, 32, 40]
+    T = 8
+    theta = _theta()
+    X, y, n, th = _make_batch(golden, lattice_grid, T, n_list, n_max, seed=10 + kid, theta=theta)
+    st = ops.gp_assemble_chol(_to(X), _to(y), _to(n), _to(th), kid)
+    best = np.array([y[t, :n[t]].max() for t in range(T)])
+    beta = 4.0
+    out = ops.grid_posterior_acq_argmax(_to(lattice_grid), _to(X), st["wfrag"], st["alpha"], _to(n), _to(th), _to(best),
+                                        kid, acq_id=acq, acq_param=beta, debug=True)
+    torch.cuda.synchronize()
+    for t in range(T):
+        nt = n[t]
+        idx, val, sto, mu, var, a = ogp.grid_step(lattice_grid, X[t, :nt], y[t, :nt], th[t], kid, acq, beta, return_fields=True)
+        mu_g = out["mu"][t].cpu().numpy(); var_g = out["var"][t].cpu().numpy(); a_g = out["acq"][t].cpu().numpy()
+        # tolerance stated by north_star: 1e-8 relative in fp64 (mean, variance); variance is a
+        # difference s - |v|^2, so its error scales with s
+        assert np.allclose(mu_g, mu, rtol=1e-8, atol=1e-8 * np.abs(mu).max()), (t, np.abs(mu_g - mu).max())
+        assert np.allclose(var_g, var, rtol=1e-8, atol=1e-10 * th[t, 2]), (t, np.abs(var_g - var).max())
+        good = np.abs(a_g - a) <= 1e-7 * np.abs(a) + 1e-9 * np.abs(a).max()
+        assert good.mean() > 0.999, (t, good.mean())
+        # next-query arg-max: bit-exact index
+        assert out["idx"][t].item() == idx, (t, out["idx"][t].item(), idx, a[idx], a[out["idx"][t].item()])
+        assert abs(out["val"][t].item() - val) <= 1e-7 * abs(val) + 1e-300
+        assert out["status"][t].item() == sto
+
+
+def test_argmax_tie_and_mask_rules(lattice_grid):
+    """Far from every observation EI underflows/flattens: ties resolve to the lowest flat index;
+    observed candidates never win; extra_mask removes candidates; all masked -> idx -1 + status."""
+    from b200bo import ops
+    n_max = 8
+    X = np.zeros((1, n_max, 2)); y = np.zeros((1, n_max)); n = np.array([2], dtype=np.int32)
+    X[0, :2] = [[0.0, 0.0], [1.0, 0.0]]
+    y[0, :2] = [5.0, 5.0]
+    th = np.array([[1e-2, 0.0, 1.0, 0.05]])        # tiny lengthscale: prior everywhere off the data
+    grid = lattice_grid[:64].copy()
+    st = ops.gp_assemble_chol(_to(X), _to(y), _to(n), _to(th), 0)
+    best = np.array([5.0])
+    out = ops.grid_posterior_acq_argmax(_to(grid), _to(X), st["wfrag"], st["alpha"], _to(n), _to(th), _to(best), 0, debug=True)
+    a = out["acq"][0].cpu().numpy()
+    assert np.all(a[2:] == a[2])                   # exact ties off the data
+    assert out["idx"][0].item() == 2               # lowest non-observed index
+    mask = np.zeros(64, dtype=np.uint8); mask[2:10] = 1
+    out = ops.grid_posterior_acq_argmax(_to(grid), _to(X), st["wfrag"], st["alpha"], _to(n), _to(th), _to(best), 0,
+                                        extra_mask=_to(mask))
+    assert out["idx"][0].item() == 10
+    out = ops.grid_posterior_acq_argmax(_to(grid), _to(X), st["wfrag"], st["alpha"], _to(n), _to(th), _to(best), 0,
+                                        extra_mask=_to(np.ones(64, dtype=np.uint8)))
+    assert out["idx"][0].item() == -1 and (out["status"][0].item() & ogp.ST_ALL_MASKED)
+    out = ops.grid_posterior_acq_argmax(_to(grid), _to(X), st["wfrag"], st["alpha"], _to(n), _to(th), _to(best), 0,
+                                        mask_observed=False, debug=True)
+    oi, _, _ = ogp.grid_step(grid, X[0, :2], y[0, :2], th[0], 0, mask_observed=False)
+    assert out["idx"][0].item() == oi
+
+
+@pytest.mark.parametrize("n_max", [16, 64, 112, 128])
+def test_large_n_and_all_template_sizes(golden, lattice_grid, n_max):
+    from b200bo import ops
+    theta = _theta()
+    X, y, n, th = _make_batch(golden, lattice_grid, 3, [n_max, n_max - 1, max(1, n_max - 9)], n_max, seed=n_max, theta=theta)
+    st = ops.gp_assemble_chol(_to(X), _to(y), _to(n), _to(th), 3)
+    best = np.array([y[t, :n[t]].max() for t in range(3)])
+    sub = lattice_grid[::3][:2000].copy()          # ragged tail: 2000 is not a multiple of 256
+    out = ops.grid_posterior_acq_argmax(_to(sub), _to(X), st["wfrag"], st["alpha"], _to(n), _to(th), _to(best), 3, debug=True)
+    for t in range(3):
+        nt = n[t]
+        idx, val, sto, mu, var, a = ogp.grid_step(sub, X[t, :nt], y[t, :nt], th[t], 3, return_fields=True)
+        assert np.allclose(out["mu"][t].cpu().numpy(), mu, rtol=1e-8, atol=1e-8 * np.abs(mu).max())
+        assert np.allclose(out["var"][t].cpu().numpy(), var, rtol=1e-8, atol=1e-9 * th[t, 2])
+        assert out["idx"][t].item() == idx
+
+
+@pytest.mark.parametrize("kid", [0, 1, 2, 3])
+def test_mll_value_and_gradient(golden, lattice_grid, kid):
+    from b200bo import ops
+    n_max = 48
+    X, y, n, _ = _make_batch(golden, lattice_grid, 10, [2, 5, 10, 20, 48], n_max, seed=kid + 50)
+    rng = np.random.default_rng(kid)
+    raw = np.stack([np.array([rng.uniform(1e-3, 3.0), rng.uniform(0, 50), rng.uniform(-2, 200), rng.uniform(-2, 15)]) for _ in range(10)])
+    raw[0] = ogp.DEFAULT_RAW
+    v, g, st = ops.mll_value_grad(_to(X), _to(y), _to(n), _to(raw), kid)
+    v = v.cpu().numpy(); g = g.cpu().numpy()
+    for t in range(10):
+        vo, go, so = ogp.mll_value_grad(X[t, :n[t]], y[t, :n[t]], raw[t], kid)
+        assert st[t].item() == so
+        assert abs(v[t] - vo) <= 1e-8 * abs(vo), (t, v[t], vo)
+        assert np.allclose(g[t], go, rtol=1e-7, atol=1e-9 * np.abs(go).max()), (t, g[t], go)
