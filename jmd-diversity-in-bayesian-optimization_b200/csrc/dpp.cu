@@ -19,7 +19,7 @@ constexpr int KREG_MAX = 12;
 // D = (sqrt(dx^2 + dy^2))^2 : scipy pdist('euclidean') then **2 (data_gen.py:489).
 __device__ __forceinline__ double dpp_entry(double ax, double ay, double bx, double by, double neg_gamma) {
   double dx = ax - bx, dy = ay - by;
-  double d = sqrt(dx * dx + dy * dy);
+  double d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));   // unfused, as numpy sums squares
   return exp(neg_gamma * (d * d));
 }
 

@@ -89,18 +89,22 @@ __device__ __forceinline__ void invert_lower(double* A, int n, int ld) {
     __syncthreads();
     double wjj = 1.0 / A[j * ld + j];
     // t[i] = sum_{k=j+1..i} W[i][k] * L[k][j]
-    double tacc[2];        // rows handled by this thread in up to 2 passes (n <= 2*rows_per_pass*... see loop)
+    double tacc[2] = {0.0, 0.0};   // rows of this thread in up to 2 passes (n <= 2 * rows_per_pass)
     int cnt = 0;
-    for (int i = j + 1 + row_in_pass; i < n; i += rows_per_pass) {
+    // block-uniform loop bounds: every lane of a warp reaches the shuffle
+    for (int ibase = j + 1; ibase < n; ibase += rows_per_pass) {
+      const int i = ibase + row_in_pass;
       double acc = 0.0;
-      for (int k = j + 1 + half; k <= i; k += 2) acc = fma(A[i * ld + k], A[k * ld + j], acc);
+      if (i < n)
+        for (int k = j + 1 + half; k <= i; k += 2) acc = fma(A[i * ld + k], A[k * ld + j], acc);
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       tacc[cnt++] = acc;
     }
     __syncthreads();
     cnt = 0;
-    for (int i = j + 1 + row_in_pass; i < n; i += rows_per_pass) {
-      if (half == 0) A[i * ld + j] = -tacc[cnt] * wjj;
+    for (int ibase = j + 1; ibase < n; ibase += rows_per_pass) {
+      const int i = ibase + row_in_pass;
+      if (i < n && half == 0) A[i * ld + j] = -tacc[cnt] * wjj;
       ++cnt;
     }
     if (threadIdx.x == 0) A[j * ld + j] = wjj;

@@ -52,16 +52,18 @@ __device__ __forceinline__ SimplexConsts simplex_consts() {
 }
 
 // SimpleNoise.py:85-172 for d = 2; vx/vy: gradient table components.
+// Python evaluates every * and + with its own rounding; __dmul_rn/__dadd_rn keep nvcc from
+// contracting them into FMAs, which is what makes the result bit-identical to the reference.
 __device__ __forceinline__ double simplex_noise_2d(double x, double y, unsigned long long hseed,
                                                    const double vx[4], const double vy[4]) {
   const SimplexConsts k = simplex_consts();
-  double s = (0.0 + x + y) * k.f;                  // sum(loc) starts from int 0
-  double fx = floor(x + s), fy = floor(y + s);
+  double s = __dmul_rn(__dadd_rn(__dadd_rn(0.0, x), y), k.f);     // sum(loc)*f, sum starts from int 0
+  double fx = floor(__dadd_rn(x, s)), fy = floor(__dadd_rn(y, s));
   long long ix = (long long)fx, iy = (long long)fy;
-  double t0 = (double)(ix + iy) * k.g;
-  double cx = x - fx + t0;                         // loc[i]-intSkewLoc[i]+t, left to right
-  double cy = y - fy + t0;
-  bool x_first = cx > cy;                          // sortWith + reverse: ties -> axis 1 first
+  double t0 = __dmul_rn((double)(ix + iy), k.g);
+  double cx = __dadd_rn(__dadd_rn(x, -fx), t0);                  // loc[i]-intSkewLoc[i]+t, left to right
+  double cy = __dadd_rn(__dadd_rn(y, -fy), t0);
+  bool x_first = cx > cy;                                        // sortWith + reverse: ties -> axis 1 first
   double n = 0.0;
   double skew = 0.0;
   long long ox = 0, oy = 0;
@@ -69,21 +71,21 @@ __device__ __forceinline__ double simplex_noise_2d(double x, double y, unsigned 
   for (int step = 0; step < 3; ++step) {
     if (step == 1) { if (x_first) ox += 1; else oy += 1; }
     if (step == 2) { if (x_first) oy += 1; else ox += 1; }
-    double ux = cx - (double)ox + skew;
-    double uy = cy - (double)oy + skew;
+    double ux = __dadd_rn(__dadd_rn(cx, -(double)ox), skew);
+    double uy = __dadd_rn(__dadd_rn(cy, -(double)oy), skew);
     double t = k.c2f;
-    t -= ux * ux;
-    t -= uy * uy;
+    t = __dadd_rn(t, -__dmul_rn(ux, ux));
+    t = __dadd_rn(t, -__dmul_rn(uy, uy));
     if (t > 0.0) {
       unsigned long long index = hseed + (unsigned long long)(ix + ox) + ((unsigned long long)(iy + oy) << 5);
-      int vi = (int)(rand_hash(index) & 3ull);     // % vecCount (= 4)
-      double gr = 0.0 + vx[vi] * ux;
-      gr = gr + vy[vi] * uy;
-      n += gr * pow4_rn(t);
+      int vi = (int)(rand_hash(index) & 3ull);                   // % vecCount (= 4)
+      double gr = __dadd_rn(0.0, __dmul_rn(vx[vi], ux));
+      gr = __dadd_rn(gr, __dmul_rn(vy[vi], uy));
+      n = __dadd_rn(n, __dmul_rn(gr, pow4_rn(t)));
     }
-    skew += k.g;
+    skew = __dadd_rn(skew, k.g);
   }
-  return n * k.scaler;
+  return __dmul_rn(n, k.scaler);
 }
 
 __device__ __forceinline__ double block_max(double v, double* sh) {
@@ -115,7 +117,7 @@ wildcat_surface_kernel(const unsigned long long* __restrict__ hseed, const int8_
   const double px = peak_xy[sidx * 2], py = peak_xy[sidx * 2 + 1];
   const double smoothness = smooth[sidx];
   const double om = 1.0 - smoothness;
-  const double fs = 100.0 * (1.0 - om * om);        // objectives.py:191  (1-smoothness)**2 == om*om exactly rounded once
+  const double fs = __dmul_rn(100.0, __dadd_rn(1.0, -__dmul_rn(om, om)));        // objectives.py:191  (1-smoothness)**2 == om*om exactly rounded once
   const double fs4 = fs / 4.0, fs8 = fs / 8.0;
   const double nstep = 100.0 / 101.0;              // np.arange(0,100,100/101), objectives.py:101
   const double var = 100.0;                        // (0.2*50)**2, objectives.py:185
@@ -124,13 +126,13 @@ wildcat_surface_kernel(const unsigned long long* __restrict__ hseed, const int8_
   for (int p = threadIdx.x; p < WW_PTS; p += WW_THREADS) {
     int iy = p / WW_SIDE, ix = p - iy * WW_SIDE;
     double dx = (double)ix - px, dy = (double)iy - py;
-    double maha = (dx * dx + dy * dy) / var;
-    double g = exp(-0.5 * (log_norm + maha));
+    double maha = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) / var;
+    double g = exp(__dmul_rn(-0.5, __dadd_rn(log_norm, maha)));
     double nx = (double)ix * nstep, ny = (double)iy * nstep;
-    double v = simplex_noise_2d(nx / fs, ny / fs, hs, vx, vy)
-             + simplex_noise_2d(nx / fs4, ny / fs4, hs, vx, vy) / 4.0
-             + simplex_noise_2d(nx / fs8, ny / fs8, hs, vx, vy) / 8.0;
-    double a = (v + 1.0) * 1.0;                    // (values+1)*N, N = 1
+    double v = __dadd_rn(__dadd_rn(simplex_noise_2d(nx / fs, ny / fs, hs, vx, vy),
+                                   simplex_noise_2d(nx / fs4, ny / fs4, hs, vx, vy) / 4.0),
+                         simplex_noise_2d(nx / fs8, ny / fs8, hs, vx, vy) / 8.0);
+    double a = __dadd_rn(v, 1.0);                  // (values+1)*N, N = 1
     gaus[p] = g;
     amp[p] = a;
     gmax = fmax(gmax, g);
@@ -144,7 +146,7 @@ wildcat_surface_kernel(const unsigned long long* __restrict__ hseed, const int8_
   const double scale = pow(10.0, power - pow(ra, 5.0));
   double smax = -INFINITY;
   for (int p = threadIdx.x; p < WW_PTS; p += WW_THREADS) {
-    double sv = gaus[p] + amp[p] * scale;
+    double sv = __dadd_rn(gaus[p], __dmul_rn(amp[p], scale));
     gaus[p] = sv;
     smax = fmax(smax, sv);
   }

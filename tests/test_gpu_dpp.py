@@ -62,13 +62,21 @@ def test_distribution_matches_reference_generate(golden):
     raw_ref_sorted = z_ref_sorted * sd_ref + mean_ref
     order = np.argsort(raw, kind="stable")
     err = np.abs(raw[order] - raw_ref_sorted) / np.abs(raw_ref_sorted)
-    assert err.max() < 1e-6, err.max()          # cond(S) up to 2.8e11 => bound 8k cond 2^-53 ~ 2.5e-3
-    assert np.median(err) < 1e-12
+    # parity bound per set: max(1e-8, 8 k cond(S) 2^-53 / |logdet|) — cond(S) reaches 2.8e11 here, the
+    # reference's own LU differs from Cholesky / 60-digit arithmetic by the same amount
+    bound = np.array([odpp.cond_bound_rel(s, gamma) for s in g["gen_s0_dist"].astype(np.float64)])
+    assert np.all(err <= bound), (err / bound).max()
+    assert err.max() < 1e-5 and np.median(err) < 1e-10, (err.max(), np.median(err))
     dev = torch.device("cuda:0")
     stats, z = ops.dpp_zscore(torch.as_tensor(raw, device=dev))
     stats = stats.cpu().numpy()
-    assert abs(stats[0] - mean_ref) <= 1e-9 * abs(mean_ref)
-    assert abs(stats[1] - sd_ref) <= 1e-9 * abs(sd_ref)
+    # the statistics kernel itself is exact to rounding on the same input ...
+    assert abs(stats[0] - raw.mean()) <= 1e-13 * abs(raw.mean())
+    assert abs(stats[1] - np.std(raw)) <= 1e-12 * np.std(raw)
+    assert np.allclose(z.cpu().numpy(), (raw - raw.mean()) / np.std(raw), rtol=1e-11, atol=1e-12)
+    # ... and against the reference it inherits the (conditioning-limited) score differences
+    assert abs(stats[0] - mean_ref) <= 1e-8 * abs(mean_ref)
+    assert abs(stats[1] - sd_ref) <= 1e-6 * abs(sd_ref)
     # chosen sets: sorted sets equal the reference's except inside near-tie groups
     dist_ref = g["gen_s0_dist"].astype(np.int64)          # (N,10,2) sorted by score
     sets_sorted = pool[pos[order]].astype(np.int64)
@@ -76,7 +84,7 @@ def test_distribution_matches_reference_generate(golden):
     bad = np.where(~same)[0]
     for b in bad:       # every mismatch must be a swap among scores closer than the parity bound
         lo, hi = max(b - 2, 0), min(b + 3, len(raw))
-        assert np.ptp(raw_ref_sorted[lo:hi]) < 2e-6 * abs(raw_ref_sorted[b]), (b, raw_ref_sorted[lo:hi])
+        assert np.ptp(raw_ref_sorted[lo:hi]) < 1e-5 * abs(raw_ref_sorted[b]), (b, raw_ref_sorted[lo:hi])
     assert len(bad) <= 20
     # sample(5) / sample(95) of the reference picked ranks `acquired`; same sets come out here
     for r, key in zip(g["gen_s0_acquired"], ("gen_s0_sample5", "gen_s0_sample95")):

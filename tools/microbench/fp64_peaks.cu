@@ -231,7 +231,7 @@ int main() {
 
   const char* lnames[5] = {"lds64_bcast", "lds64_distinct", "lds128_bcast", "lds128_distinct", "lds32_bcast"};
   float lms[5];
-  size_t smb = 8192 * sizeof(double);
+  size_t smb = 4096 * sizeof(double);
   lms[0] = time_ms([&] { k_lds<0><<<blocks, threads, smb>>>(out, 7); });
   lms[1] = time_ms([&] { k_lds<1><<<blocks, threads, smb>>>(out, 7); });
   lms[2] = time_ms([&] { k_lds<2><<<blocks, threads, smb>>>(out, 7); });
