@@ -84,11 +84,13 @@ int b200bo_simplex_noise(uint64_t hseed, const int8_t* vecs_h, const double* xy,
  * theta (T,4) f64.  Outputs (any may be NULL): L (T,n_max,n_max) lower, row-major;
  * Linv (T,n_max,n_max) = L^-1; alpha (T,n_max) = Khat^-1 (y - c); logdet (T) = log|Khat|;
  * wfrag (T, b200bo_wfrag_doubles(n_max)) = L^-1 in the MMA-fragment layout K-B consumes.
- * status (T) int32 is OR-ed into. */
+ * status (T) int32 is OR-ed into.  n[t] <= 0 marks an inactive trial (skipped).
+ * n_hint: upper bound of n[t] over this launch (0 = n_max); sizes shared memory / picks the
+ * kernel variant, so a loop whose n grows by one per iteration does not pay for n_max early. */
 size_t b200bo_wfrag_doubles(int n_max);
 int b200bo_gp_assemble_chol(const double* X, const double* y, const int32_t* n, const double* theta, double* L,
                             double* Linv, double* alpha, double* logdet, double* wfrag, int32_t* status, int T,
-                            int n_max, int kernel_id, void* stream);
+                            int n_max, int n_hint, int kernel_id, void* stream);
 
 /* ---- K-B  fused grid posterior + acquisition + arg-max --------------------------
  * replaces ExpectedImprovement(model,best_f) + optimize_acqf over the box (BO.py:158-161,
@@ -105,14 +107,32 @@ int b200bo_grid_posterior_acq_argmax(const double* grid, int G, const double* X,
                                      const double* best_f, const uint8_t* extra_mask, int mask_observed,
                                      int acq_id, double acq_param, double var_floor, int32_t* arg_idx,
                                      double* arg_val, double* mu, double* var, double* acq, int32_t* status,
-                                     int T, int n_max, int kernel_id, void* ws, size_t ws_bytes, void* stream);
+                                     int T, int n_max, int n_hint, int kernel_id, void* ws, size_t ws_bytes,
+                                     void* stream);
+
+/* Lattice variant of K-B: candidates are the nodes of a regular Gx x Gy lattice, candidate
+ * g <-> (ix = g % Gx, iy = g / Gx), x = x0 + h ix, y = y0 + h iy (data_gen.constructX,
+ * Src/data_gen.py:294-303), and every observation is a node of the same lattice (the ranked-DPP
+ * initial sets and all arg-max queries are). The kernel value then depends on (|dx|,|dy|) only and is
+ * read from ktab[slot][|dy| * Gx + |dx|] instead of being recomputed G*n times; values are
+ * bit-identical to the generic path. ktab (H,Gy,Gx) f64 from b200bo_kernel_table; ktab_id (T) int32
+ * slot per trial or NULL (slot 0). An off-lattice observation sets B200BO_ST_OFF_LATTICE. */
+int b200bo_kernel_table(const double* theta, int H, int kernel_id, double h, int TW, int TH, double* ktab, void* stream);
+int b200bo_grid_posterior_acq_argmax_lattice(int Gx, int Gy, double x0, double y0, double h, const double* ktab,
+                                             const int32_t* ktab_id, const double* X, const double* wfrag,
+                                             const double* alpha, const int32_t* n, const double* theta,
+                                             const double* best_f, const uint8_t* extra_mask, int mask_observed,
+                                             int acq_id, double acq_param, double var_floor, int32_t* arg_idx,
+                                             double* arg_val, double* mu, double* var, double* acq, int32_t* status,
+                                             int T, int n_max, int n_hint, int kernel_id, void* ws, size_t ws_bytes,
+                                             void* stream);
 
 /* ---- K-C  marginal log-likelihood value and gradient ----------------------------
  * replaces ExactMarginalLogLikelihood + autograd inside fit_gpytorch_model (BO.py:144,189).
  * raw (T,4) f64 = (noise, c, raw_outputscale, raw_lengthscale); value (T) f64 =
  * [log N(y; c, Khat) + log Gamma(noise; 1.1, 0.05)] / n ; grad (T,4) f64. */
 int b200bo_mll_value_grad(const double* X, const double* y, const int32_t* n, const double* raw, double* value,
-                          double* grad, int32_t* status, int T, int n_max, int kernel_id, void* stream);
+                          double* grad, int32_t* status, int T, int n_max, int n_hint, int kernel_id, void* stream);
 
 /* ---- batched BO loop bookkeeping (one thread per trial) ---------------------------
  * replaces the Python statements between two acquisitions in BOloop / BOloop_fixparam:

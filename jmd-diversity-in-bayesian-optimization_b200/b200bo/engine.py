@@ -1,0 +1,130 @@
+"""Batched BO engine: T independent trials advanced in lock-step on one GPU.
+
+This is the batched counterpart of ``BO.BOloop`` / ``BO.BOloop_fixparam`` (Src/BO.py:123-278,
+380-461): the reference runs one trial per process (ipyparallel / ray fan-out,
+Scripts/Experiment2.py:75-92); here the trial is the data-parallel axis of every kernel launch.
+All state lives in HBM for the whole run; the host only enqueues launches.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+
+
+@dataclass
+class BOResult:
+    yall: torch.Tensor      # (T, max_iter+2) f64 best-so-far curve, padded as BO.py:262-271
+    picked: torch.Tensor    # (T, max_iter) int32 flat candidate index per iteration, -1 = none
+    nit: torch.Tensor       # (T,) int32 iterations run
+    status: torch.Tensor    # (T,) int32 B200BO_ST_* bits
+    X: torch.Tensor         # (T, n_max, 2) f64 observations (initial set first)
+    y: torch.Tensor         # (T, n_max) f64
+    n: torch.Tensor         # (T,) int32 observations at the end
+    thetas: torch.Tensor | None = None   # (T, max_iter, 4) hyper-parameters used per iteration (fit mode)
+
+
+class BatchedBO:
+    """grid (G,2) f64 candidates; obj (S,G) f32 objective at every candidate for S surfaces; surf_id (T,)
+    which surface a trial optimises; X0 (T,n0,2) f64 and y0 (T,n0) f64 the initial sets; theta (T,4) or (4,)
+    ACTUAL hyper-parameters held fixed, or None to refit before every acquisition (``fitter``)."""
+
+    def __init__(self, grid, obj, surf_id, X0, y0, max_iter, theta=None, kernel_id=ops.MATERN52, acq_id=ops.EI,
+                 acq_param=0.0, tol=0.1, optimal_y=100.0, var_floor=ops.VAR_FLOOR, fitter=None, check_every=8,
+                 lattice="auto"):
+        dev = grid.device
+        if dev.type != "cuda":
+            raise ops._lib.B200boError("BatchedBO needs CUDA tensors: the engine has no CPU path")
+        self.grid = grid.contiguous()
+        self.obj = obj.contiguous()
+        self.T, self.n0 = y0.shape
+        self.G = grid.shape[0]
+        self.max_iter = int(max_iter)
+        self.n_max = self.n0 + self.max_iter
+        if self.n_max > ops.NMAX:
+            raise ops._lib.B200boError(f"n0 + max_iter = {self.n_max} exceeds the engine limit {ops.NMAX}")
+        T, n_max = self.T, self.n_max
+        f64, i32 = torch.float64, torch.int32
+        self.surf_id = surf_id.to(device=dev, dtype=i32).contiguous()
+        self.X = torch.zeros((T, n_max, 2), dtype=f64, device=dev)
+        self.y = torch.zeros((T, n_max), dtype=f64, device=dev)
+        self.X[:, :self.n0] = X0
+        self.y[:, :self.n0] = y0
+        self.n = torch.full((T,), self.n0, dtype=i32, device=dev)
+        self.fixed = theta is not None
+        if self.fixed:
+            th = torch.as_tensor(theta, dtype=f64, device=dev)
+            self.theta = (th.expand(T, 4) if th.dim() == 1 else th).contiguous().clone()
+        else:
+            if fitter is None:
+                raise ValueError("theta=None needs a fitter")
+            self.theta = torch.zeros((T, 4), dtype=f64, device=dev)
+        self.fitter = fitter
+        self.kernel_id, self.acq_id, self.acq_param = int(kernel_id), int(acq_id), float(acq_param)
+        self.tol, self.optimal_y, self.var_floor = float(tol), float(optimal_y), float(var_floor)
+        self.alpha = torch.zeros((T, n_max), dtype=f64, device=dev)
+        self.wfrag = torch.empty((T, ops.wfrag_doubles(n_max)), dtype=f64, device=dev)
+        self.best_f = torch.empty(T, dtype=f64, device=dev)
+        self.yall = torch.zeros((T, self.max_iter + 2), dtype=f64, device=dev)
+        self.picked = torch.empty((T, max(self.max_iter, 1)), dtype=i32, device=dev)
+        self.nit = torch.zeros(T, dtype=i32, device=dev)
+        self.status = torch.zeros(T, dtype=i32, device=dev)
+        self.arg_idx = torch.empty(T, dtype=i32, device=dev)
+        self.arg_val = torch.empty(T, dtype=f64, device=dev)
+        self.ws = ops.grid_acq_workspace(T, self.G, dev)
+        self.check_every = int(check_every)
+        # candidates on a regular lattice (data_gen.constructX) -> kernel values come from a table
+        self.lattice = ops.Lattice.from_points(self.grid) if isinstance(lattice, str) and lattice == "auto" else lattice
+        self.ktab = self.ktab_id = None
+        if self.lattice is not None:
+            if self.fixed:
+                uniq, inv = torch.unique(self.theta, dim=0, return_inverse=True)
+                self.ktab = ops.kernel_table(uniq.contiguous(), self.kernel_id, self.lattice)
+                self.ktab_id = inv.to(i32).contiguous()
+            elif T * self.G * 8 <= 8 << 30:
+                self.ktab = torch.empty((T, self.lattice.Gy, self.lattice.Gx), dtype=f64, device=dev)
+                self.ktab_id = torch.arange(T, dtype=i32, device=dev)
+            else:
+                self.lattice = None
+        self.thetas = None if self.fixed else torch.zeros((T, max(self.max_iter, 1), 4), dtype=f64, device=dev)
+        self.launches = 0
+
+    def step(self, it: int):
+        n_hint = self.n0 + it
+        if not self.fixed:
+            self.fitter.fit_into(self.X, self.y, self.n, self.kernel_id, self.theta, self.status, n_hint)
+            self.thetas[:, it] = self.theta
+            self.launches += self.fitter.last_launches
+        ops.gp_assemble_chol_into(self.X, self.y, self.n, self.theta, self.kernel_id, self.alpha, self.wfrag, self.status,
+                                  n_hint=n_hint)
+        if self.lattice is not None:
+            if not self.fixed:
+                ops.kernel_table(self.theta, self.kernel_id, self.lattice, out=self.ktab)
+                self.launches += 1
+            ops.grid_posterior_acq_argmax_lattice(self.lattice, self.ktab, self.ktab_id, self.X, self.wfrag, self.alpha,
+                                                  self.n, self.theta, self.best_f, self.kernel_id, self.acq_id,
+                                                  self.acq_param, self.var_floor, status=self.status, ws=self.ws,
+                                                  arg_idx=self.arg_idx, arg_val=self.arg_val, n_hint=n_hint)
+        else:
+            ops.grid_posterior_acq_argmax(self.grid, self.X, self.wfrag, self.alpha, self.n, self.theta, self.best_f,
+                                          self.kernel_id, self.acq_id, self.acq_param, self.var_floor,
+                                          status=self.status, ws=self.ws, arg_idx=self.arg_idx, arg_val=self.arg_val,
+                                          n_hint=n_hint)
+        ops.bo_update(self.grid, self.obj, self.surf_id, self.arg_idx, self.X, self.y, self.n, self.best_f, self.yall,
+                      self.picked, self.nit, self.max_iter, it, self.tol, self.optimal_y)
+        self.launches += 4
+
+    def run(self) -> BOResult:
+        ops.bo_init(self.y, self.n, self.best_f, self.yall, self.picked, self.nit, self.max_iter, self.tol, self.optimal_y)
+        self.launches += 1
+        for it in range(self.max_iter):
+            self.step(it)
+            if self.check_every and (it + 1) % self.check_every == 0 and it + 1 < self.max_iter:
+                if not bool((self.n > 0).any()):        # every trial reached tol: stop enqueueing
+                    break
+        ops.bo_finalize(self.yall, self.nit, self.n, self.max_iter)
+        self.launches += 1
+        return BOResult(self.yall, self.picked[:, :self.max_iter], self.nit, self.status, self.X, self.y, self.n,
+                        self.thetas)

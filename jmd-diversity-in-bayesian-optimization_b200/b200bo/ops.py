@@ -58,6 +58,8 @@ def dpp_logdet_score(pool: torch.Tensor, idx: torch.Tensor, gamma: float) -> tor
         raise _lib.B200boError("dpp_logdet_score: pool must be (P,2), idx (N,k)")
     N, k = idx.shape
     out = torch.empty(N, dtype=torch.float64, device=pool.device)
+    if N == 0:
+        return out
     check(lib.b200bo_dpp_logdet_score(_ptr(pool), pool.shape[0], _ptr(idx), N, k, float(gamma), _ptr(out), _stream()),
           "dpp_logdet_score")
     return out
@@ -117,7 +119,7 @@ def wfrag_doubles(n_max: int) -> int:
     return int(_lib.load().b200bo_wfrag_doubles(int(n_max)))
 
 
-def gp_assemble_chol(X, y, n, theta, kernel_id, want=("alpha", "wfrag"), status=None):
+def gp_assemble_chol(X, y, n, theta, kernel_id, want=("alpha", "wfrag"), status=None, n_hint=0):
     """K-A. X (T,n_max,2) f64, y (T,n_max) f64, n (T,) int32, theta (T,4) f64.
     ``want`` selects outputs among L, Linv, alpha, logdet, wfrag. Returns dict (+ status)."""
     lib = _lib.load()
@@ -136,31 +138,31 @@ def gp_assemble_chol(X, y, n, theta, kernel_id, want=("alpha", "wfrag"), status=
         status = torch.zeros(T, dtype=torch.int32, device=dev)
     check(lib.b200bo_gp_assemble_chol(_ptr(X), _ptr(y), _ptr(n), _ptr(theta), _ptr(out.get("L")), _ptr(out.get("Linv")),
                                       _ptr(out.get("alpha")), _ptr(out.get("logdet")), _ptr(out.get("wfrag")),
-                                      _ptr(status), T, n_max, int(kernel_id), _stream()), "gp_assemble_chol")
+                                      _ptr(status), T, n_max, int(n_hint), int(kernel_id), _stream()), "gp_assemble_chol")
     out["status"] = status
     return out
 
 
-def gp_assemble_chol_into(X, y, n, theta, kernel_id, alpha, wfrag, status):
+def gp_assemble_chol_into(X, y, n, theta, kernel_id, alpha, wfrag, status, n_hint=0):
     """Allocation-free K-A for the engine loop (alpha / wfrag / status preallocated)."""
     lib = _lib.load()
     T, n_max = y.shape
     check(lib.b200bo_gp_assemble_chol(_ptr(X), _ptr(y), _ptr(n), _ptr(theta), None, None, _ptr(alpha), None, _ptr(wfrag),
-                                      _ptr(status), T, n_max, int(kernel_id), _stream()), "gp_assemble_chol")
+                                      _ptr(status), T, n_max, int(n_hint), int(kernel_id), _stream()), "gp_assemble_chol")
 
 
-def mll_value_grad(X, y, n, raw, kernel_id, status=None):
+def mll_value_grad(X, y, n, raw, kernel_id, status=None, n_hint=0, value=None, grad=None):
     """K-C. raw (T,4) f64 = (noise, c, raw_outputscale, raw_lengthscale) -> value (T,), grad (T,4), status."""
     lib = _lib.load()
     _cu(X, torch.float64, "X"); _cu(y, torch.float64, "y"); _cu(n, torch.int32, "n"); _cu(raw, torch.float64, "raw")
     T, n_max = y.shape
     dev = X.device
-    value = torch.empty(T, dtype=torch.float64, device=dev)
-    grad = torch.empty((T, 4), dtype=torch.float64, device=dev)
+    if value is None: value = torch.empty(T, dtype=torch.float64, device=dev)
+    if grad is None: grad = torch.empty((T, 4), dtype=torch.float64, device=dev)
     if status is None:
         status = torch.zeros(T, dtype=torch.int32, device=dev)
     check(lib.b200bo_mll_value_grad(_ptr(X), _ptr(y), _ptr(n), _ptr(raw), _ptr(value), _ptr(grad), _ptr(status), T, n_max,
-                                    int(kernel_id), _stream()), "mll_value_grad")
+                                    int(n_hint), int(kernel_id), _stream()), "mll_value_grad")
     return value, grad, status
 
 
@@ -173,7 +175,7 @@ def grid_acq_workspace(T: int, G: int, device) -> torch.Tensor:
 
 def grid_posterior_acq_argmax(grid, X, wfrag, alpha, n, theta, best_f, kernel_id, acq_id=EI, acq_param=0.0,
                               var_floor=VAR_FLOOR, mask_observed=True, extra_mask=None, debug=False, status=None,
-                              ws=None, arg_idx=None, arg_val=None):
+                              ws=None, arg_idx=None, arg_val=None, n_hint=0):
     """K-B. Returns dict(idx (T,) int32, val (T,) f64, status[, mu, var, acq (T,G)])."""
     lib = _lib.load()
     _cu(grid, torch.float64, "grid"); _cu(X, torch.float64, "X"); _cu(wfrag, torch.float64, "wfrag")
@@ -198,9 +200,121 @@ def grid_posterior_acq_argmax(grid, X, wfrag, alpha, n, theta, best_f, kernel_id
     check(lib.b200bo_grid_posterior_acq_argmax(
         _ptr(grid), G, _ptr(X), _ptr(wfrag), _ptr(alpha), _ptr(n), _ptr(theta), _ptr(best_f), _ptr(extra_mask),
         1 if mask_observed else 0, int(acq_id), float(acq_param), float(var_floor), _ptr(arg_idx), _ptr(arg_val),
-        _ptr(mu), _ptr(var), _ptr(acq), _ptr(status), T, n_max, int(kernel_id), _ptr(ws), ws.numel(), _stream()),
+        _ptr(mu), _ptr(var), _ptr(acq), _ptr(status), T, n_max, int(n_hint), int(kernel_id), _ptr(ws), ws.numel(),
+        _stream()),
         "grid_posterior_acq_argmax")
     out = dict(idx=arg_idx, val=arg_val, status=status)
     if debug:
         out.update(mu=mu, var=var, acq=acq)
     return out
+
+
+class Lattice:
+    """Regular candidate lattice: g <-> (g % Gx, g // Gx), x = x0 + h*ix (data_gen.constructX order)."""
+
+    def __init__(self, Gx, Gy, x0=0.0, y0=0.0, h=1.0):
+        self.Gx, self.Gy, self.x0, self.y0, self.h = int(Gx), int(Gy), float(x0), float(y0), float(h)
+
+    @property
+    def G(self):
+        return self.Gx * self.Gy
+
+    def points(self, device):
+        ix = torch.arange(self.Gx, dtype=torch.float64, device=device) * self.h + self.x0
+        iy = torch.arange(self.Gy, dtype=torch.float64, device=device) * self.h + self.y0
+        return torch.stack([ix.repeat(self.Gy), iy.repeat_interleave(self.Gx)], dim=1).contiguous()
+
+    @staticmethod
+    def from_points(grid):
+        """Recognise a constructX-style lattice in a (G,2) point array (host-side, exact comparison)."""
+        g = grid.detach().cpu().numpy() if isinstance(grid, torch.Tensor) else grid
+        G = g.shape[0]
+        if G < 2:
+            return None
+        x0, y0 = float(g[0, 0]), float(g[0, 1])
+        h = float(g[1, 0] - g[0, 0])
+        if not h > 0:
+            return None
+        import numpy as np
+        row = np.nonzero(g[:, 1] != y0)[0]
+        Gx = int(row[0]) if len(row) else G
+        if G % Gx:
+            return None
+        lat = Lattice(Gx, G // Gx, x0, y0, h)
+        ix = np.arange(G) % Gx
+        iy = np.arange(G) // Gx
+        if np.array_equal(g[:, 0], x0 + h * ix) and np.array_equal(g[:, 1], y0 + h * iy):
+            return lat
+        return None
+
+
+def kernel_table(theta, kernel_id, lat: Lattice, out=None):
+    """(H,Gy,Gx) f64 table of s*k(h*sqrt(dx^2+dy^2)/l) for H hyper-parameter rows theta (H,4)."""
+    lib = _lib.load()
+    _cu(theta, torch.float64, "theta")
+    H = theta.shape[0]
+    if out is None:
+        out = torch.empty((H, lat.Gy, lat.Gx), dtype=torch.float64, device=theta.device)
+    check(lib.b200bo_kernel_table(_ptr(theta), H, int(kernel_id), lat.h, lat.Gx, lat.Gy, _ptr(out), _stream()), "kernel_table")
+    return out
+
+
+def grid_posterior_acq_argmax_lattice(lat: Lattice, ktab, ktab_id, X, wfrag, alpha, n, theta, best_f, kernel_id,
+                                      acq_id=EI, acq_param=0.0, var_floor=VAR_FLOOR, mask_observed=True,
+                                      extra_mask=None, debug=False, status=None, ws=None, arg_idx=None, arg_val=None,
+                                      n_hint=0):
+    """Lattice variant of K-B (kernel values from ``ktab``); same outputs as grid_posterior_acq_argmax."""
+    lib = _lib.load()
+    _cu(ktab, torch.float64, "ktab"); _cu(X, torch.float64, "X"); _cu(wfrag, torch.float64, "wfrag")
+    _cu(alpha, torch.float64, "alpha"); _cu(n, torch.int32, "n"); _cu(theta, torch.float64, "theta")
+    _cu(best_f, torch.float64, "best_f")
+    if ktab_id is not None:
+        _cu(ktab_id, torch.int32, "ktab_id")
+    if extra_mask is not None:
+        _cu(extra_mask, torch.uint8, "extra_mask")
+    G = lat.G
+    T, n_max = alpha.shape
+    dev = X.device
+    if ktab.shape[-2:] != (lat.Gy, lat.Gx):
+        raise _lib.B200boError("grid_posterior_acq_argmax_lattice: ktab does not match the lattice")
+    if arg_idx is None: arg_idx = torch.empty(T, dtype=torch.int32, device=dev)
+    if arg_val is None: arg_val = torch.empty(T, dtype=torch.float64, device=dev)
+    if status is None: status = torch.zeros(T, dtype=torch.int32, device=dev)
+    if ws is None: ws = grid_acq_workspace(T, G, dev)
+    mu = var = acq = None
+    if debug:
+        mu = torch.empty((T, G), dtype=torch.float64, device=dev)
+        var = torch.empty_like(mu)
+        acq = torch.empty_like(mu)
+    check(lib.b200bo_grid_posterior_acq_argmax_lattice(
+        lat.Gx, lat.Gy, lat.x0, lat.y0, lat.h, _ptr(ktab), _ptr(ktab_id), _ptr(X), _ptr(wfrag), _ptr(alpha), _ptr(n),
+        _ptr(theta), _ptr(best_f), _ptr(extra_mask), 1 if mask_observed else 0, int(acq_id), float(acq_param),
+        float(var_floor), _ptr(arg_idx), _ptr(arg_val), _ptr(mu), _ptr(var), _ptr(acq), _ptr(status), T, n_max,
+        int(n_hint), int(kernel_id), _ptr(ws), ws.numel(), _stream()), "grid_posterior_acq_argmax_lattice")
+    out = dict(idx=arg_idx, val=arg_val, status=status)
+    if debug:
+        out.update(mu=mu, var=var, acq=acq)
+    return out
+
+
+# ------------------------------------------------------------------ BO loop bookkeeping
+
+def bo_init(y, n, best_f, yall, picked, nit, max_iter, tol, optimal_y):
+    lib = _lib.load()
+    T, n_max = y.shape
+    check(lib.b200bo_bo_init(_ptr(y), _ptr(n), _ptr(best_f), _ptr(yall), _ptr(picked), _ptr(nit), T, n_max, int(max_iter),
+                             float(tol), float(optimal_y), _stream()), "bo_init")
+
+
+def bo_update(grid, obj, surf_id, arg_idx, X, y, n, best_f, yall, picked, nit, max_iter, it, tol, optimal_y):
+    lib = _lib.load()
+    T, n_max = y.shape
+    check(lib.b200bo_bo_update(_ptr(grid), grid.shape[0], _ptr(obj), _ptr(surf_id), _ptr(arg_idx), _ptr(X), _ptr(y), _ptr(n),
+                               _ptr(best_f), _ptr(yall), _ptr(picked), _ptr(nit), T, n_max, int(max_iter), int(it),
+                               float(tol), float(optimal_y), _stream()), "bo_update")
+
+
+def bo_finalize(yall, nit, n, max_iter):
+    lib = _lib.load()
+    T = nit.numel()
+    check(lib.b200bo_bo_finalize(_ptr(yall), _ptr(nit), _ptr(n), T, int(max_iter), _stream()), "bo_finalize")

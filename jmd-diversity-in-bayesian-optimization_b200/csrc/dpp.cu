@@ -195,10 +195,10 @@ extern "C" {
 int b200bo_dpp_logdet_score(const double* pool, int pool_size, const int32_t* idx, long long N, int k, double gamma,
                             double* logdet, void* stream) {
   using namespace b200bo;
-  if (!pool || !idx || !logdet) return arg_error("dpp_logdet_score: null pointer");
   if (pool_size <= 0 || k < 1 || N < 0) return arg_error("dpp_logdet_score: bad sizes pool=%d k=%d N=%lld", pool_size, k, N);
   if (k > 160) return arg_error("dpp_logdet_score: k=%d > 160 unsupported", k);
   if (N == 0) return 0;
+  if (!pool || !idx || !logdet) return arg_error("dpp_logdet_score: null pointer");
   if (N > 2147483647LL * 128) return arg_error("dpp_logdet_score: N too large");
   cudaStream_t st = as_stream(stream);
   switch (k) {

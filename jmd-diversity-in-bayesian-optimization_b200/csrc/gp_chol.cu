@@ -118,12 +118,16 @@ gp_chol_kernel(const double* __restrict__ X, const double* __restrict__ y, const
                const double* __restrict__ theta_or_raw, double* __restrict__ L_out, double* __restrict__ Linv_out,
                double* __restrict__ alpha_out, double* __restrict__ logdet_out, double* __restrict__ wfrag_out,
                double* __restrict__ mll_value, double* __restrict__ mll_grad, int32_t* __restrict__ status,
-               int n_max, int ld, int kernel_id, size_t wfrag_stride) {
+               int n_max, int n_cap, int ld, int kernel_id, size_t wfrag_stride) {
   extern __shared__ double sm[];
   const int t = blockIdx.x;
   const int n = n_arr[t];
-  if (n <= 0 || n > n_max) return;
-  CholSmem s = carve(sm, n_max, ld);
+  if (n <= 0) return;                    // inactive / finished trial
+  if (n > n_cap) {                       // caller's n_hint was too small for this trial
+    if (threadIdx.x == 0 && status) atomicOr(&status[t], B200BO_ST_CHOL_FAIL);
+    return;
+  }
+  CholSmem s = carve(sm, n_cap, ld);
   __shared__ double red[CH_THREADS / 32];
   __shared__ double sh_scalar[8];
 
@@ -223,7 +227,7 @@ gp_chol_kernel(const double* __restrict__ X, const double* __restrict__ y, const
     // fragment-major layout for mma.m8n8k4 A operands: block (I,J), J <= 2I+1, at I(I+1)+J;
     // lane l holds W[8I + l/4][4J + l%4]
     double* wf = wfrag_out + (size_t)t * wfrag_stride;
-    const int nblk = wfrag_blocks(n_max);
+    const int nblk = wfrag_blocks(n);      // K-B reads exactly this prefix for the same n
     for (int e = threadIdx.x; e < nblk * 32; e += blockDim.x) {
       int b = e >> 5, lane = e & 31;
       // invert b = I(I+1) + J
@@ -306,9 +310,10 @@ gp_chol_kernel(const double* __restrict__ X, const double* __restrict__ y, const
 
 static int launch_chol(bool mll, const double* X, const double* y, const int32_t* n, const double* th, double* L,
                        double* Linv, double* alpha, double* logdet, double* wfrag, double* value, double* grad,
-                       int32_t* status, int T, int n_max, int kernel_id, cudaStream_t st) {
-  int ld = n_max | 1;   // odd leading dimension: 2-way (= optimal for fp64) bank pattern on column walks
-  size_t smem = chol_smem_bytes(n_max, ld);
+                       int32_t* status, int T, int n_max, int n_hint, int kernel_id, cudaStream_t st) {
+  int n_cap = (n_hint > 0 && n_hint < n_max) ? n_hint : n_max;   // shared memory is sized by the largest live n
+  int ld = n_cap | 1;   // odd leading dimension: 2-way (= optimal for fp64) bank pattern on column walks
+  size_t smem = chol_smem_bytes(n_cap, ld);
   if (smem > 227 * 1024) return arg_error("gp_chol: n_max=%d needs %zu B shared memory", n_max, smem);
   size_t wstride = (size_t)wfrag_blocks(n_max) * 32;
   cudaError_t e;
@@ -316,12 +321,12 @@ static int launch_chol(bool mll, const double* X, const double* y, const int32_t
     e = cudaFuncSetAttribute(gp_chol_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e, "mll_value_grad: smem attribute");
     gp_chol_kernel<true><<<T, CH_THREADS, smem, st>>>(X, y, n, th, L, Linv, alpha, logdet, wfrag, value, grad, status,
-                                                      n_max, ld, kernel_id, wstride);
+                                                      n_max, n_cap, ld, kernel_id, wstride);
   } else {
     e = cudaFuncSetAttribute(gp_chol_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e, "gp_assemble_chol: smem attribute");
     gp_chol_kernel<false><<<T, CH_THREADS, smem, st>>>(X, y, n, th, L, Linv, alpha, logdet, wfrag, nullptr, nullptr,
-                                                       status, n_max, ld, kernel_id, wstride);
+                                                       status, n_max, n_cap, ld, kernel_id, wstride);
   }
   B200BO_CHECK_LAUNCH(mll ? "mll_value_grad" : "gp_assemble_chol");
   return 0;
@@ -335,25 +340,25 @@ size_t b200bo_wfrag_doubles(int n_max) { return (size_t)b200bo::wfrag_blocks(n_m
 
 int b200bo_gp_assemble_chol(const double* X, const double* y, const int32_t* n, const double* theta, double* L,
                             double* Linv, double* alpha, double* logdet, double* wfrag, int32_t* status, int T,
-                            int n_max, int kernel_id, void* stream) {
+                            int n_max, int n_hint, int kernel_id, void* stream) {
   using namespace b200bo;
   if (!X || !y || !n || !theta) return arg_error("gp_assemble_chol: null input pointer");
   if (T < 0 || n_max < 1 || n_max > B200BO_NMAX) return arg_error("gp_assemble_chol: T=%d n_max=%d (max %d)", T, n_max, B200BO_NMAX);
   if (kernel_id < 0 || kernel_id > 3) return arg_error("gp_assemble_chol: kernel_id=%d", kernel_id);
   if (T == 0) return 0;
-  return launch_chol(false, X, y, n, theta, L, Linv, alpha, logdet, wfrag, nullptr, nullptr, status, T, n_max, kernel_id,
-                     as_stream(stream));
+  return launch_chol(false, X, y, n, theta, L, Linv, alpha, logdet, wfrag, nullptr, nullptr, status, T, n_max, n_hint,
+                     kernel_id, as_stream(stream));
 }
 
 int b200bo_mll_value_grad(const double* X, const double* y, const int32_t* n, const double* raw, double* value,
-                          double* grad, int32_t* status, int T, int n_max, int kernel_id, void* stream) {
+                          double* grad, int32_t* status, int T, int n_max, int n_hint, int kernel_id, void* stream) {
   using namespace b200bo;
   if (!X || !y || !n || !raw || !value || !grad) return arg_error("mll_value_grad: null pointer");
   if (T < 0 || n_max < 1 || n_max > B200BO_NMAX) return arg_error("mll_value_grad: T=%d n_max=%d (max %d)", T, n_max, B200BO_NMAX);
   if (kernel_id < 0 || kernel_id > 3) return arg_error("mll_value_grad: kernel_id=%d", kernel_id);
   if (T == 0) return 0;
   return launch_chol(true, X, y, n, raw, nullptr, nullptr, nullptr, nullptr, nullptr, value, grad, status, T, n_max,
-                     kernel_id, as_stream(stream));
+                     n_hint, kernel_id, as_stream(stream));
 }
 
 }  // extern "C"

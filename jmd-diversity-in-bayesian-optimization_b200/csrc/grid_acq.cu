@@ -53,12 +53,19 @@ struct GridAcqParams {
   double* acq_out;
   int32_t* status;          // (T)
   int n_max;
+  int n_cap;                // upper bound of n[t] over the launch (template / smem selection)
   size_t wstride;
   int chunks;
   int cols_per_cta;         // multiple of 32
+  // lattice variant: candidates g <-> (g % Gx, g / Gx), x = x0 + h * ix; kernel values come from
+  // ktab[slot][|dy| * Gx + |dx|] (built by kernel_table_kernel with the same device function)
+  int Gx, Gy;
+  double x0, y0, h;
+  const double* ktab;       // (H, Gy, Gx)
+  const int32_t* ktab_id;   // (T) table slot per trial, or null = slot 0
 };
 
-template <int KID, int NI_MAX>
+template <int KID, int NI_MAX, bool LATTICE>
 __global__ void __launch_bounds__(GA_THREADS, (NI_MAX <= 8 ? 2 : 1))
 grid_acq_kernel(const GridAcqParams p) {
   extern __shared__ double sm[];
@@ -66,6 +73,14 @@ grid_acq_kernel(const GridAcqParams p) {
   const int chunk = blockIdx.x - t * p.chunks;
   const int n = p.n[t];
   if (n <= 0) return;                     // finished / inactive trial (uniform per CTA)
+  if (n > p.n_cap || n > 8 * NI_MAX) {    // n_hint too small: report, do not touch memory
+    if (threadIdx.x == 0) {
+      p.part_val[(size_t)t * p.chunks + chunk] = -INFINITY;
+      p.part_idx[(size_t)t * p.chunks + chunk] = INT_MAX;
+      if (p.status) atomicOr(&p.status[t], B200BO_ST_ALL_MASKED);
+    }
+    return;
+  }
   const int nI = (n + 7) >> 3;
   const int nJ = 2 * nI;
   const int npad = 8 * nI;
@@ -76,6 +91,8 @@ grid_acq_kernel(const GridAcqParams p) {
   double* xs = sm + (size_t)nblk * 32;    // npad
   double* ys = xs + npad;
   double* al = ys + npad;
+  int* xi = reinterpret_cast<int*>(al + npad);   // lattice coordinates (LATTICE only), npad each
+  int* yi = xi + npad;
   __shared__ double red_val[GA_WARPS];
   __shared__ int red_idx[GA_WARPS];
   __shared__ int red_flag;
@@ -89,9 +106,18 @@ grid_acq_kernel(const GridAcqParams p) {
       xs[j] = v ? p.X[((size_t)t * p.n_max + j) * 2] : 0.0;
       ys[j] = v ? p.X[((size_t)t * p.n_max + j) * 2 + 1] : 0.0;
       al[j] = v ? p.alpha[(size_t)t * p.n_max + j] : 0.0;
+      if (LATTICE) {
+        const double fx = rint((xs[j] - p.x0) / p.h), fy = rint((ys[j] - p.y0) / p.h);
+        const bool on = (p.x0 + p.h * fx == xs[j]) && (p.y0 + p.h * fy == ys[j]) && fx >= 0.0 && fy >= 0.0 &&
+                        fx < (double)p.Gx && fy < (double)p.Gy;
+        xi[j] = on ? (int)fx : 0;
+        yi[j] = on ? (int)fy : 0;
+        if (v && !on && p.status) atomicOr(&p.status[t], B200BO_ST_OFF_LATTICE);
+      }
     }
     if (threadIdx.x == 0) red_flag = 0;
   }
+  const double* tab = LATTICE ? p.ktab + (size_t)(p.ktab_id ? p.ktab_id[t] : 0) * p.Gx * p.Gy : nullptr;
   const double cst = p.theta[(size_t)t * 4 + 1];
   const double sc = p.theta[(size_t)t * 4 + 2];
   const double ell = p.theta[(size_t)t * 4 + 3];
@@ -114,36 +140,68 @@ grid_acq_kernel(const GridAcqParams p) {
 #pragma unroll 1
     for (int q = 0; q < 4; ++q) {
       const int gb = min(base + 8 * q + bcol, p.G - 1);
-      const double2 gp = __ldg(&p.grid[gb]);
       double kval[2 * NI_MAX];
       double mu_part = 0.0;
       int masked = 0;
+      if (LATTICE) {
+        const int gyi = gb / p.Gx, gxi = gb - gyi * p.Gx;
 #pragma unroll
-      for (int J = 0; J < 2 * NI_MAX; ++J) {
-        kval[J] = 0.0;
-        if (J < nJ) {
-          const int j = 4 * J + jrow;
-          const double dx = gp.x - xs[j], dy = gp.y - ys[j];
-          const double r2 = dx * dx + dy * dy;
-          double kv = kernel_from_r2<KID>(r2, sc, ell, kp.a_scale);
-          const bool valid = j < n;
-          kv = valid ? kv : 0.0;
-          masked |= (valid && r2 == 0.0) ? 1 : 0;
-          kval[J] = kv;
-          mu_part = fma(kv, al[j], mu_part);
+        for (int J = 0; J < 2 * NI_MAX; ++J) {
+          kval[J] = 0.0;
+          if (J < nJ) {
+            const int j = 4 * J + jrow;
+            const int dxi = abs(gxi - xi[j]), dyi = abs(gyi - yi[j]);
+            double kv = __ldg(&tab[dyi * p.Gx + dxi]);
+            const bool valid = j < n;
+            kv = valid ? kv : 0.0;
+            masked |= (valid && (dxi | dyi) == 0) ? 1 : 0;
+            kval[J] = kv;
+            mu_part = fma(kv, al[j], mu_part);
+          }
+        }
+      } else {
+        const double2 gp = __ldg(&p.grid[gb]);
+#pragma unroll
+        for (int J = 0; J < 2 * NI_MAX; ++J) {
+          kval[J] = 0.0;
+          if (J < nJ) {
+            const int j = 4 * J + jrow;
+            const double dx = gp.x - xs[j], dy = gp.y - ys[j];
+            const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            double kv = kernel_from_r2<KID>(r2, sc, ell, kp.a_scale);
+            const bool valid = j < n;
+            kv = valid ? kv : 0.0;
+            masked |= (valid && r2 == 0.0) ? 1 : 0;
+            kval[J] = kv;
+            mu_part = fma(kv, al[j], mu_part);
+          }
         }
       }
       // V = L^-1 K* on the FP64 MMA path; accumulate squared entries per C column
       double ss0 = 0.0, ss1 = 0.0;
 #pragma unroll
-      for (int I = 0; I < NI_MAX; ++I) {
+      for (int I = 0; I < NI_MAX; I += 2) {
         if (I < nI) {
-          double c0 = 0.0, c1 = 0.0;
-          const double* wrow = wsm + (size_t)(I * (I + 1)) * 32 + lane;
+          // two independent accumulator chains (row blocks I and I+1) keep the FP64 MMA pipe fed
+          double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+          const double* w0 = wsm + (size_t)(I * (I + 1)) * 32 + lane;
+          const double* w1 = wsm + (size_t)((I + 1) * (I + 2)) * 32 + lane;
+          if (I + 1 < nI) {
 #pragma unroll
-          for (int J = 0; J <= 2 * I + 1; ++J) dmma_m8n8k4(c0, c1, wrow[J * 32], kval[J]);
-          ss0 = fma(c0, c0, ss0);
-          ss1 = fma(c1, c1, ss1);
+            for (int J = 0; J <= 2 * I + 1; ++J) {
+              dmma_m8n8k4(a0, a1, w0[J * 32], kval[J]);
+              dmma_m8n8k4(b0, b1, w1[J * 32], kval[J]);
+            }
+            dmma_m8n8k4(b0, b1, w1[(2 * I + 2) * 32], kval[2 * I + 2]);
+            dmma_m8n8k4(b0, b1, w1[(2 * I + 3) * 32], kval[2 * I + 3]);
+            ss0 = fma(b0, b0, ss0);
+            ss1 = fma(b1, b1, ss1);
+          } else {
+#pragma unroll
+            for (int J = 0; J <= 2 * I + 1; ++J) dmma_m8n8k4(a0, a1, w0[J * 32], kval[J]);
+          }
+          ss0 = fma(a0, a0, ss0);
+          ss1 = fma(a1, a1, ss1);
         }
       }
       // rows live in lane>>2: reduce over xor 4, 8, 16
@@ -240,26 +298,45 @@ inline int pick_chunks(int T, int G) {
   return want > max_chunks ? max_chunks : want;
 }
 
-template <int KID, int NI_MAX>
+inline size_t grid_acq_smem(int nI) {
+  return ((size_t)nI * (nI + 1) * 32 + 3 * 8 * (size_t)nI) * sizeof(double) + 2 * 8 * (size_t)nI * sizeof(int);
+}
+
+template <int KID, int NI_MAX, bool LATTICE>
 static int launch_grid_acq(const GridAcqParams& p, int T, cudaStream_t st) {
-  const int nI = NI_MAX;
-  size_t smem = ((size_t)nI * (nI + 1) * 32 + 3 * 8 * (size_t)nI) * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(grid_acq_kernel<KID, NI_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  size_t smem = grid_acq_smem(NI_MAX);
+  cudaError_t e = cudaFuncSetAttribute(grid_acq_kernel<KID, NI_MAX, LATTICE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e, "grid_posterior_acq_argmax: smem attribute");
   // dynamic smem sized by the largest n actually possible in this instantiation would waste
   // occupancy for small n; size it by n_max rounded to the tile instead.
-  int nIa = (p.n_max + 7) / 8;
+  int nIa = (p.n_cap + 7) / 8;
   if (nIa > NI_MAX) nIa = NI_MAX;
-  smem = ((size_t)nIa * (nIa + 1) * 32 + 3 * 8 * (size_t)nIa) * sizeof(double);
-  grid_acq_kernel<KID, NI_MAX><<<(unsigned)((size_t)T * p.chunks), GA_THREADS, smem, st>>>(p);
+  smem = grid_acq_smem(nIa);
+  grid_acq_kernel<KID, NI_MAX, LATTICE><<<(unsigned)((size_t)T * p.chunks), GA_THREADS, smem, st>>>(p);
   return 0;
 }
 
-template <int KID>
+template <int KID, bool LATTICE>
 static int dispatch_ni(const GridAcqParams& p, int T, cudaStream_t st) {
-  if (p.n_max <= 32) return launch_grid_acq<KID, 4>(p, T, st);
-  if (p.n_max <= 64) return launch_grid_acq<KID, 8>(p, T, st);
-  return launch_grid_acq<KID, 16>(p, T, st);
+  if (p.n_cap <= 32) return launch_grid_acq<KID, 4, LATTICE>(p, T, st);
+  if (p.n_cap <= 64) return launch_grid_acq<KID, 8, LATTICE>(p, T, st);
+  return launch_grid_acq<KID, 16, LATTICE>(p, T, st);
+}
+
+// ktab[slot][dy * TW + dx] = s k(h sqrt(dx^2 + dy^2) / l): the same device function and the same
+// operand values the generic path sees for lattice points, so both variants agree bit for bit.
+__global__ void __launch_bounds__(256)
+kernel_table_kernel(const double* __restrict__ theta, int H, int kernel_id, double h, int TW, int TH,
+                    double* __restrict__ ktab) {
+  const int slot = blockIdx.y;
+  const double sc = theta[(size_t)slot * 4 + 2], ell = theta[(size_t)slot * 4 + 3];
+  const KernParams kp = make_kern_params(sc, ell, kernel_id);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < TW * TH; e += gridDim.x * blockDim.x) {
+    const int dyi = e / TW, dxi = e - dyi * TW;
+    const double dx = h * (double)dxi, dy = h * (double)dyi;
+    const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    ktab[(size_t)slot * TW * TH + e] = kernel_from_r2_dyn(kernel_id, r2, sc, ell, kp.a_scale);
+  }
 }
 
 }  // namespace b200bo
@@ -272,22 +349,26 @@ size_t b200bo_grid_acq_workspace_bytes(int T, int G) {
   return (size_t)T * chunks * (sizeof(double) + sizeof(int32_t)) + 16;
 }
 
-int b200bo_grid_posterior_acq_argmax(const double* grid, int G, const double* X, const double* wfrag,
-                                     const double* alpha, const int32_t* n, const double* theta,
-                                     const double* best_f, const uint8_t* extra_mask, int mask_observed, int acq_id,
-                                     double acq_param, double var_floor, int32_t* arg_idx, double* arg_val, double* mu,
-                                     double* var, double* acq, int32_t* status, int T, int n_max, int kernel_id,
-                                     void* ws, size_t ws_bytes, void* stream) {
+static int grid_acq_common(bool lattice, const double* grid, int G, int Gx, int Gy, double x0, double y0, double h,
+                           const double* ktab, const int32_t* ktab_id, const double* X, const double* wfrag,
+                           const double* alpha, const int32_t* n, const double* theta, const double* best_f,
+                           const uint8_t* extra_mask, int mask_observed, int acq_id, double acq_param,
+                           double var_floor, int32_t* arg_idx, double* arg_val, double* mu, double* var, double* acq,
+                           int32_t* status, int T, int n_max, int n_hint, int kernel_id, void* ws, size_t ws_bytes,
+                           void* stream) {
   using namespace b200bo;
-  if (!grid || !X || !wfrag || !alpha || !n || !theta || !best_f || !arg_idx || !ws)
-    return arg_error("grid_posterior_acq_argmax: null pointer");
+  const char* who = lattice ? "grid_posterior_acq_argmax_lattice" : "grid_posterior_acq_argmax";
   if (T < 0 || G < 1 || n_max < 1 || n_max > B200BO_NMAX)
-    return arg_error("grid_posterior_acq_argmax: T=%d G=%d n_max=%d (max %d)", T, G, n_max, B200BO_NMAX);
-  if (kernel_id < 0 || kernel_id > 3) return arg_error("grid_posterior_acq_argmax: kernel_id=%d", kernel_id);
-  if (acq_id < 0 || acq_id > 2) return arg_error("grid_posterior_acq_argmax: acq_id=%d", acq_id);
-  if (acq_id == B200BO_ACQ_UCB && !(acq_param >= 0.0)) return arg_error("grid_posterior_acq_argmax: UCB beta < 0");
-  if (ws_bytes < b200bo_grid_acq_workspace_bytes(T, G)) return arg_error("grid_posterior_acq_argmax: workspace too small");
+    return arg_error("%s: T=%d G=%d n_max=%d (max %d)", who, T, G, n_max, B200BO_NMAX);
   if (T == 0) return 0;
+  if ((!lattice && !grid) || !X || !wfrag || !alpha || !n || !theta || !best_f || !arg_idx || !ws)
+    return arg_error("%s: null pointer", who);
+  if (lattice && (!ktab || Gx < 1 || Gy < 1 || (long long)Gx * Gy != G || !(h > 0.0)))
+    return arg_error("%s: bad lattice Gx=%d Gy=%d h=%g", who, Gx, Gy, h);
+  if (kernel_id < 0 || kernel_id > 3) return arg_error("%s: kernel_id=%d", who, kernel_id);
+  if (acq_id < 0 || acq_id > 2) return arg_error("%s: acq_id=%d", who, acq_id);
+  if (acq_id == B200BO_ACQ_UCB && !(acq_param >= 0.0)) return arg_error("%s: UCB beta < 0", who);
+  if (ws_bytes < b200bo_grid_acq_workspace_bytes(T, G)) return arg_error("%s: workspace too small", who);
   cudaStream_t st = as_stream(stream);
   GridAcqParams p;
   p.grid = reinterpret_cast<const double2*>(grid);
@@ -305,18 +386,60 @@ int b200bo_grid_posterior_acq_argmax(const double* grid, int G, const double* X,
   p.mu_out = mu; p.var_out = var; p.acq_out = acq;
   p.status = status;
   p.n_max = n_max;
+  p.n_cap = (n_hint > 0 && n_hint < n_max) ? n_hint : n_max;
   p.wstride = b200bo_wfrag_doubles(n_max);
+  p.Gx = Gx; p.Gy = Gy; p.x0 = x0; p.y0 = y0; p.h = h; p.ktab = ktab; p.ktab_id = ktab_id;
   int rc;
-  switch (kernel_id) {
-    case B200BO_KERNEL_RBF: rc = dispatch_ni<B200BO_KERNEL_RBF>(p, T, st); break;
-    case B200BO_KERNEL_MATERN12: rc = dispatch_ni<B200BO_KERNEL_MATERN12>(p, T, st); break;
-    case B200BO_KERNEL_MATERN32: rc = dispatch_ni<B200BO_KERNEL_MATERN32>(p, T, st); break;
-    default: rc = dispatch_ni<B200BO_KERNEL_MATERN52>(p, T, st); break;
+  if (lattice) {
+    // table look-ups do not depend on the kernel family: one instantiation serves all four
+    rc = dispatch_ni<B200BO_KERNEL_MATERN52, true>(p, T, st);
+  } else {
+    switch (kernel_id) {
+      case B200BO_KERNEL_RBF: rc = dispatch_ni<B200BO_KERNEL_RBF, false>(p, T, st); break;
+      case B200BO_KERNEL_MATERN12: rc = dispatch_ni<B200BO_KERNEL_MATERN12, false>(p, T, st); break;
+      case B200BO_KERNEL_MATERN32: rc = dispatch_ni<B200BO_KERNEL_MATERN32, false>(p, T, st); break;
+      default: rc = dispatch_ni<B200BO_KERNEL_MATERN52, false>(p, T, st); break;
+    }
   }
   if (rc) return rc;
-  B200BO_CHECK_LAUNCH("grid_posterior_acq_argmax");
+  B200BO_CHECK_LAUNCH(who);
   argmax_finish_kernel<<<(T + 127) / 128, 128, 0, st>>>(p.part_val, p.part_idx, p.chunks, T, n, arg_idx, arg_val, status);
-  B200BO_CHECK_LAUNCH("grid_posterior_acq_argmax: finish");
+  B200BO_CHECK_LAUNCH(who);
+  return 0;
+}
+
+int b200bo_grid_posterior_acq_argmax(const double* grid, int G, const double* X, const double* wfrag,
+                                     const double* alpha, const int32_t* n, const double* theta,
+                                     const double* best_f, const uint8_t* extra_mask, int mask_observed, int acq_id,
+                                     double acq_param, double var_floor, int32_t* arg_idx, double* arg_val, double* mu,
+                                     double* var, double* acq, int32_t* status, int T, int n_max, int n_hint,
+                                     int kernel_id, void* ws, size_t ws_bytes, void* stream) {
+  return grid_acq_common(false, grid, G, 0, 0, 0.0, 0.0, 1.0, nullptr, nullptr, X, wfrag, alpha, n, theta, best_f,
+                         extra_mask, mask_observed, acq_id, acq_param, var_floor, arg_idx, arg_val, mu, var, acq, status,
+                         T, n_max, n_hint, kernel_id, ws, ws_bytes, stream);
+}
+
+int b200bo_grid_posterior_acq_argmax_lattice(int Gx, int Gy, double x0, double y0, double h, const double* ktab,
+                                             const int32_t* ktab_id, const double* X, const double* wfrag,
+                                             const double* alpha, const int32_t* n, const double* theta,
+                                             const double* best_f, const uint8_t* extra_mask, int mask_observed,
+                                             int acq_id, double acq_param, double var_floor, int32_t* arg_idx,
+                                             double* arg_val, double* mu, double* var, double* acq, int32_t* status,
+                                             int T, int n_max, int n_hint, int kernel_id, void* ws, size_t ws_bytes,
+                                             void* stream) {
+  return grid_acq_common(true, nullptr, Gx * Gy, Gx, Gy, x0, y0, h, ktab, ktab_id, X, wfrag, alpha, n, theta, best_f,
+                         extra_mask, mask_observed, acq_id, acq_param, var_floor, arg_idx, arg_val, mu, var, acq, status,
+                         T, n_max, n_hint, kernel_id, ws, ws_bytes, stream);
+}
+
+int b200bo_kernel_table(const double* theta, int H, int kernel_id, double h, int TW, int TH, double* ktab, void* stream) {
+  using namespace b200bo;
+  if (!theta || !ktab) return arg_error("kernel_table: null pointer");
+  if (H < 1 || TW < 1 || TH < 1 || !(h > 0.0) || H > 65535) return arg_error("kernel_table: bad sizes H=%d TW=%d TH=%d", H, TW, TH);
+  if (kernel_id < 0 || kernel_id > 3) return arg_error("kernel_table: kernel_id=%d", kernel_id);
+  dim3 grid((TW * TH + 255) / 256 > 64 ? 64 : (TW * TH + 255) / 256, H);
+  kernel_table_kernel<<<grid, 256, 0, as_stream(stream)>>>(theta, H, kernel_id, h, TW, TH, ktab);
+  B200BO_CHECK_LAUNCH("kernel_table");
   return 0;
 }
 

@@ -1,0 +1,70 @@
+"""GPU parity: the batched BO loop (BOloop_fixparam semantics on a grid) vs the oracle loop —
+selected indices bit-exact, best-so-far curves identical, padding as BO.py:262-271."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import AUTHOR_THETA_RAW
+from oracle import gp as ogp
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _setup(golden, lattice_grid, T, n0, seed):
+    g = golden("wildcat.npz")
+    surfs = np.stack([g["surf_0"], g["surf_1"], g["surf_2"], g["surf_3"]])
+    obj = surfs[:, :100, :100].reshape(4, -1).astype(np.float32)      # objective at lattice nodes
+    rng = np.random.default_rng(seed)
+    surf_id = rng.integers(0, 4, T).astype(np.int32)
+    idx0 = np.stack([rng.choice(10000, n0, replace=False) for _ in range(T)])
+    X0 = lattice_grid[idx0]
+    y0 = np.stack([obj[surf_id[t], idx0[t]] for t in range(T)]).astype(np.float64)
+    return obj, surf_id, X0, y0
+
+
+@pytest.mark.parametrize("lattice", ["auto", None])
+@pytest.mark.parametrize("kid,acq", [(3, 0), (0, 0), (3, 1)])
+def test_fixed_theta_loop_matches_oracle(golden, lattice_grid, kid, acq, lattice):
+    from b200bo import engine
+    T, n0, max_iter = 12, 10, 25
+    obj, surf_id, X0, y0 = _setup(golden, lattice_grid, T, n0, seed=kid * 10 + acq)
+    theta = ogp.raw_to_theta(AUTHOR_THETA_RAW)
+    t = lambda a, dt=None: torch.as_tensor(a, device=DEV, dtype=dt)
+    bo = engine.BatchedBO(t(lattice_grid), t(obj), t(surf_id), t(X0), t(y0), max_iter, theta=t(theta), kernel_id=kid,
+                          acq_id=acq, acq_param=4.0, tol=0.1, lattice=lattice)
+    assert (bo.lattice is not None) == (lattice == "auto")
+    res = bo.run()
+    torch.cuda.synchronize()
+    yall = res.yall.cpu().numpy(); picked = res.picked.cpu().numpy(); nit = res.nit.cpu().numpy()
+    assert yall.shape == (T, max_iter + 2)
+    early = 0
+    for i in range(T):
+        o = ogp.bo_loop(lattice_grid, obj[surf_id[i]], X0[i], y0[i], max_iter, theta=theta, kernel_id=kid, acq_id=acq,
+                        acq_param=4.0, tol=0.1)
+        assert nit[i] == o["nit"], (i, nit[i], o["nit"])
+        assert np.array_equal(picked[i, :nit[i]], o["idx"]), (i, picked[i, :nit[i]], o["idx"])
+        assert np.all(picked[i, nit[i]:] == -1)
+        assert np.array_equal(yall[i], o["yall"])
+        assert res.n[i].item() == n0 + nit[i]
+        assert np.array_equal(res.X[i, :n0 + nit[i]].cpu().numpy(), o["X"])
+        early += nit[i] < max_iter
+    assert res.status.max().item() == 0
+    if acq == 0 and kid == 3:
+        assert early > 0          # tol = 0.1 stops trials that reach the optimum (BO.py:152)
+
+
+def test_tol_disabled_runs_all_iterations_and_never_repeats_a_point(golden, lattice_grid):
+    from b200bo import engine
+    T, n0, max_iter = 64, 10, 40
+    obj, surf_id, X0, y0 = _setup(golden, lattice_grid, T, n0, seed=99)
+    theta = ogp.raw_to_theta(AUTHOR_THETA_RAW)
+    t = lambda a: torch.as_tensor(a, device=DEV)
+    res = engine.BatchedBO(t(lattice_grid), t(obj), t(surf_id), t(X0), t(y0), max_iter, theta=t(theta), tol=-1.0).run()
+    assert torch.all(res.nit == max_iter)
+    X = res.X.cpu().numpy()
+    for i in range(T):
+        assert len({tuple(p) for p in X[i]}) == n0 + max_iter          # observed candidates are masked
+    yall = res.yall.cpu().numpy()
+    assert np.all(np.diff(yall, axis=1) >= 0)                          # best-so-far is monotone
+    assert np.array_equal(yall[:, -1], yall[:, -2])                    # final append (BO.py:262)

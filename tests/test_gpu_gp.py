@@ -61,7 +61,7 @@ def test_assemble_chol_alpha_linv(golden, lattice_grid, kid):
         assert abs(out["logdet"][t].item() - ld) <= 1e-10 * abs(ld) + 1e-12
         # fragment layout: block (I,J) at I(I+1)+J, lane l -> W[8I + l/4][4J + l%4]
         wf = out["wfrag"][t].cpu().numpy()
-        nI = (n_max + 7) // 8
+        nI = (nt + 7) // 8                      # only the prefix for the trial's own n is written
         for I in range(nI):
             for J in range(2 * I + 2):
                 blk = wf[(I * (I + 1) + J) * 32:(I * (I + 1) + J + 1) * 32]
@@ -181,3 +181,56 @@ def test_mll_value_and_gradient(golden, lattice_grid, kid):
         assert st[t].item() == so
         assert abs(v[t] - vo) <= 1e-8 * abs(vo), (t, v[t], vo)
         assert np.allclose(g[t], go, rtol=1e-7, atol=1e-9 * np.abs(go).max()), (t, g[t], go)
+
+
+@pytest.mark.parametrize("kid", [0, 1, 2, 3])
+def test_lattice_variant_is_bit_identical_to_generic(golden, lattice_grid, kid):
+    """Table look-ups replace G*n kernel evaluations on a lattice; values must not change at all."""
+    from b200bo import ops
+    n_max = 72
+    T = 6
+    rng = np.random.default_rng(kid)
+    X, y, n, th = _make_batch(golden, lattice_grid, T, [5, 10, 33, 64, 72, 1], n_max, seed=kid + 7)
+    th[3:] = th[0]                                     # trials 0,3,4,5 share a table slot
+    uniq, inv = np.unique(th, axis=0, return_inverse=True)
+    st = ops.gp_assemble_chol(_to(X), _to(y), _to(n), _to(th), kid)
+    best = np.array([y[t, :n[t]].max() for t in range(T)])
+    grid = _to(lattice_grid)
+    lat = ops.Lattice.from_points(grid)
+    assert (lat.Gx, lat.Gy, lat.x0, lat.y0, lat.h) == (100, 100, 0.0, 0.0, 1.0)
+    assert torch.equal(lat.points(grid.device), grid)
+    ktab = ops.kernel_table(_to(uniq), kid, lat)
+    a = ops.grid_posterior_acq_argmax(grid, _to(X), st["wfrag"], st["alpha"], _to(n), _to(th), _to(best), kid, debug=True)
+    b = ops.grid_posterior_acq_argmax_lattice(lat, ktab, _to(inv.astype(np.int32)), _to(X), st["wfrag"], st["alpha"], _to(n),
+                                              _to(th), _to(best), kid, debug=True)
+    for key in ("mu", "var", "acq", "idx", "val", "status"):
+        assert torch.equal(a[key], b[key]), key
+
+
+def test_lattice_half_step_grid_and_off_lattice_flag(golden):
+    """constructX(budget=40000): 200x200 nodes, step 0.5 (BASELINE config 4 candidates)."""
+    from b200bo import ops
+    ax = np.arange(0, 100, 0.5)
+    grid = np.stack(np.meshgrid(ax, ax), axis=-1).reshape(-1, 2)
+    lat = ops.Lattice.from_points(grid)
+    assert (lat.Gx, lat.Gy, lat.h) == (200, 200, 0.5)
+    rng = np.random.default_rng(3)
+    n_max = 24
+    X = np.zeros((2, n_max, 2)); y = np.zeros((2, n_max)); n = np.array([20, 24], dtype=np.int32)
+    for t in range(2):
+        X[t, :n[t]] = grid[rng.choice(40000, n[t], replace=False)]
+        y[t, :n[t]] = rng.uniform(0, 100, n[t])
+    th = np.tile(_theta(), (2, 1))
+    st = ops.gp_assemble_chol(_to(X), _to(y), _to(n), _to(th), 3)
+    best = np.array([y[t, :n[t]].max() for t in range(2)])
+    ktab = ops.kernel_table(_to(th[:1]), 3, lat)
+    b = ops.grid_posterior_acq_argmax_lattice(lat, ktab, None, _to(X), st["wfrag"], st["alpha"], _to(n), _to(th), _to(best), 3, debug=True)
+    for t in range(2):
+        idx, val, sto, mu, var, a = ogp.grid_step(grid, X[t, :n[t]], y[t, :n[t]], th[t], 3, return_fields=True)
+        assert np.allclose(b["mu"][t].cpu().numpy(), mu, rtol=1e-8, atol=1e-8 * np.abs(mu).max())
+        assert np.allclose(b["var"][t].cpu().numpy(), var, rtol=1e-8, atol=1e-10 * th[t, 2])
+        assert b["idx"][t].item() == idx and b["status"][t].item() == 0
+    X[1, 3] += 0.25                                     # not a node any more
+    st = ops.gp_assemble_chol(_to(X), _to(y), _to(n), _to(th), 3)
+    b = ops.grid_posterior_acq_argmax_lattice(lat, ktab, None, _to(X), st["wfrag"], st["alpha"], _to(n), _to(th), _to(best), 3)
+    assert b["status"][0].item() == 0 and (b["status"][1].item() & ops.ST_OFF_LATTICE)
