@@ -50,6 +50,11 @@ const char* b200bo_last_error_string(void);
 /* sm_count / cc of the current device; returns cudaError_t */
 int b200bo_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* FP64 FMA issue-rate probe (roofline denominator measured on the GPU the benchmark runs on):
+ * launches blocks x 256 threads x iters x 8 dependent-chain FMAs, writes blocks*256 doubles to out,
+ * returns the flop count issued (> 0) or -(error code). */
+long long b200bo_fp64_fma_probe(double* out, int blocks, int iters, void* stream);
+
 /* ---- K-D  ranked-DPP set score -------------------------------------------------
  * replaces diverse_data_generator.twoD_score looped over the superset,
  * Src/data_gen.py:484-497 called from :403.
@@ -64,6 +69,14 @@ size_t b200bo_dpp_stats_workspace_bytes(long long N);
 int b200bo_dpp_zscore(const double* logdet, long long N, double* stats, double* z, void* ws, size_t ws_bytes,
                       void* stream);
 
+/* combinadic un-ranking: m-th k-subset of range(n) in lexicographic order, 128-bit ranks.
+ * replaces combination_finder.find_elm (Src/Combination.py:131-170) looped at data_gen.py:392.
+ * binom_lo/hi (k, n+1) uint64: C(v,b) for b = 1..k (row b-1), v = 0..n; m_lo/hi (N) ranks;
+ * total = C(n,k) (must be < 2^128). out (N,k) int32 ascending indices; rank >= total -> row of -1
+ * (the reference raises there). */
+int b200bo_unrank_u128(const uint64_t* binom_lo, const uint64_t* binom_hi, const uint64_t* m_lo, const uint64_t* m_hi,
+                       uint64_t total_lo, uint64_t total_hi, int n, int k, long long N, int32_t* out, void* stream);
+
 /* ---- K-E  Wildcat Wells --------------------------------------------------------
  * replaces objectives.wildcatwells (Src/objectives.py:107-218, N = 1 peak, d = 2) and the
  * 10 201 x 3 SimplexNoise.simplexNoise calls inside it (Src/SimpleNoise.py:85-172).
@@ -73,6 +86,11 @@ int b200bo_dpp_zscore(const double* logdet, long long N, double* stats, double* 
  * surf (S,101,101) f32 out, row-major [iy][ix], max == 100. */
 int b200bo_wildcat_surface(const uint64_t* hseed, const int8_t* vecs, const double* peak_xy, const double* smooth,
                            const double* rug_amp, float* surf, int S, void* stream);
+/* objective evaluation f(x) of generate_cont() (Src/objectives.py:322-351, LinearNDInterpolator over the
+ * 101x101 nodes): surf (S,101,101) f32, surf_id (M) int32 or NULL (surface 0), xy (M,2) f64 -> out (M) f64.
+ * Node values are exact; inside a cell the main-diagonal triangulation is used; NaN outside [0,100]^2. */
+int b200bo_wildcat_eval(const float* surf, const int32_t* surf_id, const double* xy, double* out, long long M,
+                        void* stream);
 /* raw simplex noise at M points (M,2) f64 for one (hseed, vecs): SimpleNoise.py:85-172 */
 int b200bo_simplex_noise(uint64_t hseed, const int8_t* vecs_h, const double* xy, double* out, long long M,
                          void* stream);
@@ -133,6 +151,21 @@ int b200bo_grid_posterior_acq_argmax_lattice(int Gx, int Gy, double x0, double y
  * [log N(y; c, Khat) + log Gamma(noise; 1.1, 0.05)] / n ; grad (T,4) f64. */
 int b200bo_mll_value_grad(const double* X, const double* y, const int32_t* n, const double* raw, double* value,
                           double* grad, int32_t* status, int T, int n_max, int n_hint, int kernel_id, void* stream);
+
+/* ---- batched hyper-parameter fit driver -------------------------------------------------
+ * replaces botorch.fit.fit_gpytorch_model (scipy L-BFGS-B over the 4 raw parameters with the
+ * bound noise >= 1e-4), Src/BO.py:144,189. One optimiser state machine per trial; the caller
+ * alternates b200bo_mll_value_grad(raw = xt, n = n_eval) and b200bo_lbfgs_step until n_eval is 0
+ * everywhere. state: b200bo_lbfgs_state_bytes(T) bytes; xt (T,4) current evaluation points (in: start);
+ * raw0 (4) shared or (T,4) per-trial start; n_obs (T) observations per trial (<= 0: trial skipped);
+ * outputs on convergence: theta_out (T,4) actual values, raw_out (T,4), mll_out (T), iters_out (T,2)
+ * = {iterations, evaluations}. */
+size_t b200bo_lbfgs_state_bytes(int T);
+int b200bo_lbfgs_init(void* state, double* xt, const double* raw0, int raw0_per_trial, int32_t* n_eval,
+                      const int32_t* n_obs, int T, double lb_noise, void* stream);
+int b200bo_lbfgs_step(void* state, double* xt, const double* value, const double* grad, int32_t* n_eval,
+                      const int32_t* n_obs, double* theta_out, double* raw_out, double* mll_out, int32_t* iters_out,
+                      int T, double lb_noise, double gtol, double ftol, int max_iter, int max_ls, void* stream);
 
 /* ---- batched BO loop bookkeeping (one thread per trial) ---------------------------
  * replaces the Python statements between two acquisitions in BOloop / BOloop_fixparam:

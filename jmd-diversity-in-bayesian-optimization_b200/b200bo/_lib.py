@@ -22,7 +22,10 @@ PROTOTYPES = {
     "b200bo_dpp_logdet_score": (c_int, [P, c_int, P, c_longlong, c_int, c_double, P, P]),
     "b200bo_dpp_stats_workspace_bytes": (c_size_t, [c_longlong]),
     "b200bo_dpp_zscore": (c_int, [P, c_longlong, P, P, P, c_size_t, P]),
+    "b200bo_unrank_u128": (c_int, [P, P, P, P, c_uint64, c_uint64, c_int, c_int, c_longlong, P, P]),
     "b200bo_wildcat_surface": (c_int, [P, P, P, P, P, P, c_int, P]),
+    "b200bo_fp64_fma_probe": (c_longlong, [P, c_int, c_int, P]),
+    "b200bo_wildcat_eval": (c_int, [P, P, P, P, c_longlong, P]),
     "b200bo_simplex_noise": (c_int, [c_uint64, P, P, P, c_longlong, P]),
     "b200bo_wfrag_doubles": (c_size_t, [c_int]),
     "b200bo_gp_assemble_chol": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
@@ -34,6 +37,9 @@ PROTOTYPES = {
                                                          P, c_int, c_int, c_double, c_double, P, P, P, P, P, P, c_int,
                                                          c_int, c_int, c_int, P, c_size_t, P]),
     "b200bo_mll_value_grad": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    "b200bo_lbfgs_state_bytes": (c_size_t, [c_int]),
+    "b200bo_lbfgs_init": (c_int, [P, P, P, c_int, P, P, c_int, c_double, P]),
+    "b200bo_lbfgs_step": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_double, c_double, c_double, c_int, c_int, P]),
     "b200bo_bo_init": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_double, c_double, P]),
     "b200bo_bo_update": (c_int, [P, c_int, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_double,
                                  c_double, P]),

@@ -90,6 +90,16 @@ class BatchedBO:
                 self.lattice = None
         self.thetas = None if self.fixed else torch.zeros((T, max(self.max_iter, 1), 4), dtype=f64, device=dev)
         self.launches = 0
+        self.profile = None        # set to a list to collect (name, n, start_event, end_event) per launch
+
+    def _timed(self, name, n, fn):
+        if self.profile is None:
+            return fn()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        self.profile.append((name, n, e0, e1))
 
     def step(self, it: int):
         n_hint = self.n0 + it
@@ -97,8 +107,14 @@ class BatchedBO:
             self.fitter.fit_into(self.X, self.y, self.n, self.kernel_id, self.theta, self.status, n_hint)
             self.thetas[:, it] = self.theta
             self.launches += self.fitter.last_launches
-        ops.gp_assemble_chol_into(self.X, self.y, self.n, self.theta, self.kernel_id, self.alpha, self.wfrag, self.status,
-                                  n_hint=n_hint)
+        self._timed("gp_chol", n_hint, lambda: ops.gp_assemble_chol_into(
+            self.X, self.y, self.n, self.theta, self.kernel_id, self.alpha, self.wfrag, self.status, n_hint=n_hint))
+        self._timed("grid_acq", n_hint, lambda: self._acquire(n_hint))
+        ops.bo_update(self.grid, self.obj, self.surf_id, self.arg_idx, self.X, self.y, self.n, self.best_f, self.yall,
+                      self.picked, self.nit, self.max_iter, it, self.tol, self.optimal_y)
+        self.launches += 4
+
+    def _acquire(self, n_hint):
         if self.lattice is not None:
             if not self.fixed:
                 ops.kernel_table(self.theta, self.kernel_id, self.lattice, out=self.ktab)
@@ -112,9 +128,6 @@ class BatchedBO:
                                           self.kernel_id, self.acq_id, self.acq_param, self.var_floor,
                                           status=self.status, ws=self.ws, arg_idx=self.arg_idx, arg_val=self.arg_val,
                                           n_hint=n_hint)
-        ops.bo_update(self.grid, self.obj, self.surf_id, self.arg_idx, self.X, self.y, self.n, self.best_f, self.yall,
-                      self.picked, self.nit, self.max_iter, it, self.tol, self.optimal_y)
-        self.launches += 4
 
     def run(self) -> BOResult:
         ops.bo_init(self.y, self.n, self.best_f, self.yall, self.picked, self.nit, self.max_iter, self.tol, self.optimal_y)

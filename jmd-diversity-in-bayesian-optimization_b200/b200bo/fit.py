@@ -1,0 +1,71 @@
+"""Batched GP hyper-parameter fitting on device: K-C (value + gradient of the marginal likelihood)
+driven by one projected L-BFGS state machine per trial (csrc/lbfgs.cu).
+
+Host role: enqueue `mll_value_grad` + `lbfgs_step` rounds; a device-side flag array tells which trials
+still need evaluations, and the host polls it every ``poll`` rounds only to stop enqueueing early.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, ops
+from ._lib import check
+
+DEFAULT_RAW = (2.0, 0.0, 0.0, 0.0)   # fresh gpytorch defaults every fit (BO.py:176-181): noise 2, c 0, raw_s = raw_l = 0
+NOISE_LB = 1e-4                      # botorch default GaussianLikelihood: GreaterThan(1e-4) handed to L-BFGS-B
+
+
+class LBFGSFitter:
+    def __init__(self, T: int, device, raw0=DEFAULT_RAW, gtol=1e-5, ftol=2.220446049250313e-9, max_iter=200,
+                 max_ls=30, max_rounds=600, poll=8):
+        lib = _lib.load()
+        self.T = int(T)
+        dev = torch.device(device)
+        self.state = torch.zeros(max(int(lib.b200bo_lbfgs_state_bytes(self.T)), 8), dtype=torch.uint8, device=dev)
+        self.xt = torch.empty((self.T, 4), dtype=torch.float64, device=dev)
+        self.value = torch.empty(self.T, dtype=torch.float64, device=dev)
+        self.grad = torch.empty((self.T, 4), dtype=torch.float64, device=dev)
+        self.n_eval = torch.empty(self.T, dtype=torch.int32, device=dev)
+        self.raw = torch.empty((self.T, 4), dtype=torch.float64, device=dev)
+        self.mll = torch.empty(self.T, dtype=torch.float64, device=dev)
+        self.iters = torch.zeros((self.T, 2), dtype=torch.int32, device=dev)
+        self.kc_status = torch.zeros(self.T, dtype=torch.int32, device=dev)
+        r0 = torch.as_tensor(raw0, dtype=torch.float64, device=dev)
+        self.raw0 = r0.contiguous()
+        self.raw0_per_trial = 1 if r0.dim() == 2 else 0
+        self.gtol, self.ftol, self.max_iter, self.max_ls = float(gtol), float(ftol), int(max_iter), int(max_ls)
+        self.max_rounds, self.poll = int(max_rounds), int(poll)
+        self.last_launches = 0
+        self.last_rounds = 0
+
+    def fit_into(self, X, y, n, kernel_id, theta_out, status=None, n_hint=0):
+        """Fit every trial with n[t] > 0 from the default start; writes ACTUAL theta (T,4) into theta_out."""
+        lib = _lib.load()
+        p, s = ops._ptr, ops._stream()
+        T = self.T
+        check(lib.b200bo_lbfgs_init(p(self.state), p(self.xt), p(self.raw0), self.raw0_per_trial, p(self.n_eval), p(n), T,
+                                    NOISE_LB, s), "lbfgs_init")
+        launches = 1
+        rounds = 0
+        n_max = y.shape[1]
+        while rounds < self.max_rounds:
+            check(lib.b200bo_mll_value_grad(p(X), p(y), p(self.n_eval), p(self.xt), p(self.value), p(self.grad),
+                                            p(self.kc_status), T, n_max, int(n_hint), int(kernel_id), s), "mll_value_grad")
+            check(lib.b200bo_lbfgs_step(p(self.state), p(self.xt), p(self.value), p(self.grad), p(self.n_eval), p(n),
+                                        p(theta_out), p(self.raw), p(self.mll), p(self.iters), T, NOISE_LB, self.gtol,
+                                        self.ftol, self.max_iter, self.max_ls, s), "lbfgs_step")
+            launches += 2
+            rounds += 1
+            if rounds % self.poll == 0 and not bool((self.n_eval > 0).any()):
+                break
+        else:
+            # round budget exhausted: one more evaluation and a forced finish so every trial reports
+            check(lib.b200bo_mll_value_grad(p(X), p(y), p(self.n_eval), p(self.xt), p(self.value), p(self.grad),
+                                            p(self.kc_status), T, n_max, int(n_hint), int(kernel_id), s), "mll_value_grad")
+            check(lib.b200bo_lbfgs_step(p(self.state), p(self.xt), p(self.value), p(self.grad), p(self.n_eval), p(n),
+                                        p(theta_out), p(self.raw), p(self.mll), p(self.iters), T, NOISE_LB, self.gtol,
+                                        self.ftol, self.max_iter, -1, s), "lbfgs_step")
+            launches += 2
+        self.last_launches = launches
+        self.last_rounds = rounds
+        return theta_out

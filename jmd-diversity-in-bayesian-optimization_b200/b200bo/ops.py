@@ -78,6 +78,55 @@ def dpp_zscore(logdet: torch.Tensor):
     return stats, z
 
 
+_BINOM_CACHE = {}
+
+
+def _binom_table(n: int, k: int, device):
+    """(lo, hi) uint64-as-int64 tensors (k, n+1): C(v,b), b = 1..k, v = 0..n, plus C(n,k)."""
+    import math
+    import numpy as np
+    key = (n, k, str(device))
+    if key not in _BINOM_CACHE:
+        total = math.comb(n, k)
+        if total >= 1 << 128:
+            raise _lib.B200boError(f"C({n},{k}) does not fit 128 bits; use the host un-ranker (Combination.py)")
+        lo = np.zeros((k, n + 1), dtype=np.uint64)
+        hi = np.zeros((k, n + 1), dtype=np.uint64)
+        mask = (1 << 64) - 1
+        for b in range(1, k + 1):
+            c = 0                      # C(v,b) by the recurrence C(v+1,b) = C(v,b) (v+1)/(v+1-b)
+            for v in range(n + 1):
+                c = 0 if v < b else (1 if v == b else c * v // (v - b))
+                if c >> 128:
+                    c_store = (1 << 128) - 1        # saturate: never <= x (x < C(n,k) < 2^128)
+                else:
+                    c_store = c
+                lo[b - 1, v] = c_store & mask
+                hi[b - 1, v] = c_store >> 64
+        _BINOM_CACHE[key] = (torch.as_tensor(lo.view(np.int64), device=device), torch.as_tensor(hi.view(np.int64), device=device), total)
+    return _BINOM_CACHE[key]
+
+
+def unrank(n: int, k: int, ranks, device) -> torch.Tensor:
+    """Lexicographic un-ranking of Python-int ranks -> (N,k) int32 index sets (on device)."""
+    import numpy as np
+    lib = _lib.load()
+    lo_t, hi_t, total = _binom_table(n, k, device)
+    mask = (1 << 64) - 1
+    N = len(ranks)
+    m_lo = np.fromiter(((int(r) & mask) for r in ranks), dtype=np.uint64, count=N)
+    m_hi = np.fromiter(((int(r) >> 64) for r in ranks), dtype=np.uint64, count=N)
+    if any(int(r) < 0 or int(r) >> 128 for r in ranks):
+        raise _lib.B200boError("unrank: rank out of the 128-bit range")
+    mlo = torch.as_tensor(m_lo.view(np.int64), device=device)
+    mhi = torch.as_tensor(m_hi.view(np.int64), device=device)
+    out = torch.empty((N, k), dtype=torch.int32, device=device)
+    if N:
+        check(lib.b200bo_unrank_u128(_ptr(lo_t), _ptr(hi_t), _ptr(mlo), _ptr(mhi), total & mask, total >> 64, n, k, N,
+                                     _ptr(out), _stream()), "unrank_u128")
+    return out
+
+
 # ------------------------------------------------------------------ K-E
 
 def wildcat_surface(hseed: torch.Tensor, vecs: torch.Tensor, peak_xy: torch.Tensor, smooth: torch.Tensor,
@@ -97,6 +146,40 @@ def wildcat_surface(hseed: torch.Tensor, vecs: torch.Tensor, peak_xy: torch.Tens
     check(lib.b200bo_wildcat_surface(_ptr(hseed), _ptr(vecs), _ptr(peak_xy), _ptr(smooth), _ptr(rug_amp), _ptr(surf), S,
                                      _stream()), "wildcat_surface")
     return surf
+
+
+def wildcat_eval(surf: torch.Tensor, xy: torch.Tensor, surf_id=None) -> torch.Tensor:
+    """f(x) for M points xy (M,2) f64 on surfaces surf (S,101,101) f32; surf_id (M,) int32 or None."""
+    lib = _lib.load()
+    _cu(surf, torch.float32, "surf"); _cu(xy, torch.float64, "xy")
+    if surf_id is not None:
+        _cu(surf_id, torch.int32, "surf_id")
+    M = xy.shape[0]
+    out = torch.empty(M, dtype=torch.float64, device=xy.device)
+    if M:
+        check(lib.b200bo_wildcat_eval(_ptr(surf), _ptr(surf_id), _ptr(xy), _ptr(out), M, _stream()), "wildcat_eval")
+    return out
+
+
+def fp64_fma_peak_tflops(device=None, reps=5) -> float:
+    """Measured FP64 FMA throughput of the current GPU in TFLOP/s (best of ``reps``, CUDA events)."""
+    lib = _lib.load()
+    dev = torch.device(device or "cuda")
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    blocks, iters = sms * 8, 4096
+    out = torch.empty(blocks * 256, dtype=torch.float64, device=dev)
+    best = 0.0
+    for r in range(reps + 2):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        flops = lib.b200bo_fp64_fma_probe(_ptr(out), blocks, iters, _stream())
+        e1.record()
+        e1.synchronize()
+        if flops <= 0:
+            raise _lib.B200boError("fp64_fma_probe failed: " + lib.b200bo_last_error_string().decode())
+        if r >= 2:
+            best = max(best, flops / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
 
 
 def simplex_noise(hseed: int, vecs, xy: torch.Tensor) -> torch.Tensor:

@@ -30,7 +30,34 @@ int cuda_status(cudaError_t e, const char* where) {
 
 }  // namespace b200bo
 
+namespace b200bo {
+// FP64 FMA issue-rate probe: 8 independent chains per thread, `iters` x 8 FMAs each. Gives the roofline
+// denominator for the FP64-bound kernels on the very GPU a benchmark runs on (DMMA shares this pipe:
+// tools/microbench/fp64_peaks.cu).
+__global__ void __launch_bounds__(256) fp64_fma_probe_kernel(double* out, int iters, double a, double b) {
+  double acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = threadIdx.x * 1e-3 + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fma(acc[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace b200bo
+
 extern "C" {
+
+long long b200bo_fp64_fma_probe(double* out, int blocks, int iters, void* stream) {
+  if (!out || blocks < 1 || iters < 1) return b200bo::arg_error("fp64_fma_probe: bad arguments");
+  b200bo::fp64_fma_probe_kernel<<<blocks, 256, 0, b200bo::as_stream(stream)>>>(out, iters, 1.0000001, 1e-9);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return -(long long)b200bo::cuda_status(e, "fp64_fma_probe");
+  return (long long)blocks * 256 * iters * 8 * 2;   // flops issued
+}
 
 const char* b200bo_version(void) { return "b200bo 0.1.0 (sm_100a)"; }
 

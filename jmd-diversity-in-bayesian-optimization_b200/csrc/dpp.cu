@@ -245,3 +245,60 @@ int b200bo_dpp_zscore(const double* logdet, long long N, double* stats, double* 
 }
 
 }  // extern "C"
+
+// ---- combinadic un-ranking on device ------------------------------
+// Replaces combination_finder.find_elm (Src/Combination.py:131-170), 93 % of the reference's
+// generate() wall time (pure-Python big integers). 128-bit unsigned arithmetic covers
+// C(10000,10) ~ 2.7e33 < 2^112; the binomials C(v,b), v <= n, b <= k come from a host-built
+// table (b-major), the per-position search is a binary search for the largest v < a with
+// C(v,b) <= x, exactly the quantity LargestV / LargestV_binary return.
+namespace b200bo {
+
+typedef unsigned __int128 u128;
+
+__global__ void __launch_bounds__(128)
+unrank_u128_kernel(const unsigned long long* __restrict__ binom_lo, const unsigned long long* __restrict__ binom_hi,
+                   const unsigned long long* __restrict__ m_lo, const unsigned long long* __restrict__ m_hi,
+                   unsigned long long tot_lo, unsigned long long tot_hi, int n, int k, long long N,
+                   int32_t* __restrict__ out) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const u128 total = ((u128)tot_hi << 64) | tot_lo;       // C(n,k)
+  const u128 m = ((u128)m_hi[i] << 64) | m_lo[i];
+  if (m >= total) {                                        // m == C(n,k): the reference raises (Combination.py:150-153)
+    for (int p = 0; p < k; ++p) out[i * k + p] = -1;
+    return;
+  }
+  u128 x = (total - 1) - m;
+  int a = n;
+  for (int b = k; b >= 1; --b) {
+    const unsigned long long* lo = binom_lo + (size_t)(b - 1) * (n + 1);
+    const unsigned long long* hi = binom_hi + (size_t)(b - 1) * (n + 1);
+    int l = b - 1, h = a - 1;                              // C(b-1,b) = 0 <= x
+    while (l < h) {
+      int mid = (l + h + 1) >> 1;
+      u128 c = ((u128)__ldg(&hi[mid]) << 64) | __ldg(&lo[mid]);
+      if (c <= x) l = mid; else h = mid - 1;
+    }
+    x -= ((u128)__ldg(&hi[l]) << 64) | __ldg(&lo[l]);
+    out[i * k + (k - b)] = (n - 1) - l;
+    a = l;
+  }
+}
+
+}  // namespace b200bo
+
+extern "C" int b200bo_unrank_u128(const uint64_t* binom_lo, const uint64_t* binom_hi, const uint64_t* m_lo,
+                                  const uint64_t* m_hi, uint64_t total_lo, uint64_t total_hi, int n, int k, long long N,
+                                  int32_t* out, void* stream) {
+  using namespace b200bo;
+  if (N < 0 || n < 1 || k < 1 || k > n) return arg_error("unrank_u128: bad sizes n=%d k=%d N=%lld", n, k, N);
+  if (N == 0) return 0;
+  if (!binom_lo || !binom_hi || !m_lo || !m_hi || !out) return arg_error("unrank_u128: null pointer");
+  unrank_u128_kernel<<<(unsigned)((N + 127) / 128), 128, 0, as_stream(stream)>>>(
+      reinterpret_cast<const unsigned long long*>(binom_lo), reinterpret_cast<const unsigned long long*>(binom_hi),
+      reinterpret_cast<const unsigned long long*>(m_lo), reinterpret_cast<const unsigned long long*>(m_hi),
+      total_lo, total_hi, n, k, N, out);
+  B200BO_CHECK_LAUNCH("unrank_u128");
+  return 0;
+}

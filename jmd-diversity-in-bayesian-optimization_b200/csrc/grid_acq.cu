@@ -23,7 +23,7 @@
 
 namespace b200bo {
 
-constexpr int GA_THREADS = 256;
+constexpr int GA_THREADS = 128;
 constexpr int GA_WARPS = GA_THREADS / 32;
 
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
@@ -66,7 +66,7 @@ struct GridAcqParams {
 };
 
 template <int KID, int NI_MAX, bool LATTICE>
-__global__ void __launch_bounds__(GA_THREADS, (NI_MAX <= 8 ? 2 : 1))
+__global__ void __launch_bounds__(GA_THREADS, (NI_MAX <= 8 ? 4 : 3))
 grid_acq_kernel(const GridAcqParams p) {
   extern __shared__ double sm[];
   const int t = blockIdx.x / p.chunks;
@@ -83,7 +83,7 @@ grid_acq_kernel(const GridAcqParams p) {
   }
   const int nI = (n + 7) >> 3;
   const int nJ = 2 * nI;
-  const int npad = 8 * nI;
+  const int npad = (8 * nI + 31) & ~31;   // look-ups run in chunks of 8 k-blocks = 32 observations
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nblk = nI * (nI + 1);
 
@@ -91,8 +91,7 @@ grid_acq_kernel(const GridAcqParams p) {
   double* xs = sm + (size_t)nblk * 32;    // npad
   double* ys = xs + npad;
   double* al = ys + npad;
-  int* xi = reinterpret_cast<int*>(al + npad);   // lattice coordinates (LATTICE only), npad each
-  int* yi = xi + npad;
+  int* xyi = reinterpret_cast<int*>(al + npad);  // packed lattice coordinates x | y << 16 (LATTICE only)
   __shared__ double red_val[GA_WARPS];
   __shared__ int red_idx[GA_WARPS];
   __shared__ int red_flag;
@@ -110,8 +109,7 @@ grid_acq_kernel(const GridAcqParams p) {
         const double fx = rint((xs[j] - p.x0) / p.h), fy = rint((ys[j] - p.y0) / p.h);
         const bool on = (p.x0 + p.h * fx == xs[j]) && (p.y0 + p.h * fy == ys[j]) && fx >= 0.0 && fy >= 0.0 &&
                         fx < (double)p.Gx && fy < (double)p.Gy;
-        xi[j] = on ? (int)fx : 0;
-        yi[j] = on ? (int)fy : 0;
+        xyi[j] = on ? ((int)fx | ((int)fy << 16)) : 0;
         if (v && !on && p.status) atomicOr(&p.status[t], B200BO_ST_OFF_LATTICE);
       }
     }
@@ -145,18 +143,26 @@ grid_acq_kernel(const GridAcqParams p) {
       int masked = 0;
       if (LATTICE) {
         const int gyi = gb / p.Gx, gxi = gb - gyi * p.Gx;
+        // chunks of 8 k-blocks: 8 index computations, then 8 independent table loads in flight,
+        // then 8 FMAs — one uniform branch per chunk instead of one per look-up
 #pragma unroll
-        for (int J = 0; J < 2 * NI_MAX; ++J) {
-          kval[J] = 0.0;
-          if (J < nJ) {
-            const int j = 4 * J + jrow;
-            const int dxi = abs(gxi - xi[j]), dyi = abs(gyi - yi[j]);
-            double kv = __ldg(&tab[dyi * p.Gx + dxi]);
-            const bool valid = j < n;
-            kv = valid ? kv : 0.0;
-            masked |= (valid && (dxi | dyi) == 0) ? 1 : 0;
-            kval[J] = kv;
-            mu_part = fma(kv, al[j], mu_part);
+        for (int Jb = 0; Jb < 2 * NI_MAX; Jb += 8) {
+          if (Jb < nJ) {
+            int kix[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int j = 4 * (Jb + u) + jrow;
+              const int pk = xyi[j];
+              const int dxi = abs(gxi - (pk & 0xffff)), dyi = abs(gyi - (pk >> 16));
+              kix[u] = dyi * p.Gx + dxi;
+              masked |= (kix[u] == 0 && j < n) ? 1 : 0;     // dxi < Gx, so 0 <=> dxi == dyi == 0
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) kval[Jb + u] = __ldg(tab + kix[u]);
+            // padded observations (j >= n) hit columns of L^-1 that are zero and alpha = 0: any finite
+            // table value is harmless there
+#pragma unroll
+            for (int u = 0; u < 8; ++u) mu_part = fma(kval[Jb + u], al[4 * (Jb + u) + jrow], mu_part);
           }
         }
       } else {
@@ -292,14 +298,15 @@ argmax_finish_kernel(const double* __restrict__ part_val, const int32_t* __restr
 }
 
 inline int pick_chunks(int T, int G) {
-  int max_chunks = (G + 255) / 256;
+  int max_chunks = (G + GA_THREADS - 1) / GA_THREADS;
   int want = (4 * 148 + T - 1) / T;
   if (want < 1) want = 1;
   return want > max_chunks ? max_chunks : want;
 }
 
 inline size_t grid_acq_smem(int nI) {
-  return ((size_t)nI * (nI + 1) * 32 + 3 * 8 * (size_t)nI) * sizeof(double) + 2 * 8 * (size_t)nI * sizeof(int);
+  size_t npad = ((size_t)8 * nI + 31) & ~(size_t)31;
+  return ((size_t)nI * (nI + 1) * 32 + 3 * npad) * sizeof(double) + npad * sizeof(int);
 }
 
 template <int KID, int NI_MAX, bool LATTICE>
@@ -380,7 +387,7 @@ static int grid_acq_common(bool lattice, const double* grid, int G, int Gx, int 
   p.acq_param = acq_id == B200BO_ACQ_UCB ? sqrt(acq_param) : acq_param;
   p.var_floor = var_floor;
   p.chunks = pick_chunks(T, G);
-  p.cols_per_cta = (((G + p.chunks - 1) / p.chunks + 255) / 256) * 256;
+  p.cols_per_cta = (((G + p.chunks - 1) / p.chunks + GA_THREADS - 1) / GA_THREADS) * GA_THREADS;
   p.part_val = reinterpret_cast<double*>(ws);
   p.part_idx = reinterpret_cast<int32_t*>(p.part_val + (size_t)T * p.chunks);
   p.mu_out = mu; p.var_out = var; p.acq_out = acq;

@@ -166,9 +166,50 @@ simplex_noise_kernel(unsigned long long hseed, double v0x, double v0y, double v1
   }
 }
 
+// Piecewise-linear evaluation of a surface between lattice nodes. At nodes the value is the fp32 node
+// value exactly, as the reference's LinearNDInterpolator gives (objectives.py:349-350; SURVEY.md
+// Appendix C). Inside a unit cell Qhull's Delaunay split is arbitrary (both diagonals are valid for a
+// square); this engine fixes the main diagonal (0,0)-(1,1) — a documented own convention.
+// Outside [0,100]^2: NaN, as the interpolator's fill value.
+__global__ void __launch_bounds__(256)
+wildcat_eval_kernel(const float* __restrict__ surf, const int32_t* __restrict__ surf_id, const double2* __restrict__ xy,
+                    double* __restrict__ out, long long M) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x) {
+    const double2 p = xy[i];
+    const float* s = surf + (size_t)(surf_id ? surf_id[i] : 0) * WW_PTS;
+    double r;
+    if (!(p.x >= 0.0 && p.x <= 100.0 && p.y >= 0.0 && p.y <= 100.0)) {
+      r = nan("");
+    } else {
+      int jx = (int)floor(p.x), iy = (int)floor(p.y);
+      if (jx > 99) jx = 99;
+      if (iy > 99) iy = 99;
+      const double u = p.x - jx, v = p.y - iy;
+      const double v00 = s[iy * WW_SIDE + jx], v10 = s[iy * WW_SIDE + jx + 1];
+      const double v01 = s[(iy + 1) * WW_SIDE + jx], v11 = s[(iy + 1) * WW_SIDE + jx + 1];
+      if (u == 0.0 && v == 0.0) r = v00;
+      else if (u >= v) r = v00 + u * (v10 - v00) + v * (v11 - v10);
+      else r = v00 + v * (v01 - v00) + u * (v11 - v01);
+    }
+    out[i] = r;
+  }
+}
+
 }  // namespace b200bo
 
 extern "C" {
+
+int b200bo_wildcat_eval(const float* surf, const int32_t* surf_id, const double* xy, double* out, long long M, void* stream) {
+  using namespace b200bo;
+  if (M < 0) return arg_error("wildcat_eval: M=%lld", M);
+  if (M == 0) return 0;
+  if (!surf || !xy || !out) return arg_error("wildcat_eval: null pointer");
+  long long blocks = (M + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  wildcat_eval_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(surf, surf_id, reinterpret_cast<const double2*>(xy), out, M);
+  B200BO_CHECK_LAUNCH("wildcat_eval");
+  return 0;
+}
 
 int b200bo_wildcat_surface(const uint64_t* hseed, const int8_t* vecs, const double* peak_xy, const double* smooth,
                            const double* rug_amp, float* surf, int S, void* stream) {

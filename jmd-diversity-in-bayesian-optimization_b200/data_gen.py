@@ -1,0 +1,293 @@
+"""Drop-in for the reference's ``Src/data_gen.py`` (ranked-DPP "subDPP" sampler).
+
+``diverse_data_generator`` keeps the reference's attributes (X, gamma, training_size, options, data,
+key, acquiredsets, mean, sd, tracker, rng) and methods (constructX, generate, sample, twoD_score,
+compare_subDPP, iid_comb_locs).  What changes underneath:
+
+* the element ranks are still drawn by CPython's / numpy's generators exactly as the reference does
+  (data_gen.py:853-880) — they decide which sets exist, so parity of *chosen sets* depends on them;
+* un-ranking (93 % of the reference's wall time, Combination.py) runs on the GPU in 128-bit integers;
+* scoring  log det exp(-gamma D)  (data_gen.py:484-497), the mean / std / z-score block (:406-408) run in
+  CUDA kernels (csrc/dpp.cu); the argsort (:409) is a stable device sort.
+
+Out of scope: the vanilla k-DPP eigendecomposition baseline and the on-disk CSV /
+ray mode.
+"""
+import random
+import string
+import time
+
+import numpy as np
+import torch
+
+from Combination import combination_finder
+from b200bo import host, ops
+
+
+class diverse_data_generator:
+    def __init__(self):
+        self.acquiredsets = []
+        self.data = {}
+        self.gamma = None
+        self.X = None
+        self._training_size = None
+        self.rng = None
+        self._key = None
+        self._dim = None
+        self.mean = None
+        self.sd = None
+        self.tracker = {"N_results": 0, "time-tracking": {}}
+        self.options = {"GPU": True, "parallel-process": True, "seed": None, "N_samples": 10000, "bounds": None,
+                        "time-debug": False, "local_dir": None}
+        self.gamma_correlation_dict = {}
+        self.combination_sampler = combination_finder()
+        self.device = "cuda:0"
+        self._X_dev = None
+
+    # ------------------------------------------------------------------ bookkeeping (data_gen.py:110-171)
+    @property
+    def key(self):
+        return self._key
+
+    @key.setter
+    def key(self, seed):
+        if isinstance(seed, int):
+            raise Exception("Seed for keygen can only be an int, not {}".format(type(seed)))
+        random.seed(seed)
+        self._key = "".join(random.choice(string.ascii_letters) for _ in range(8))
+        self.create_data_dict()
+
+    @property
+    def training_size(self):
+        return self._training_size
+
+    @training_size.setter
+    def training_size(self, value):
+        self.gamma_correlation_dict = None
+        self._training_size = int(value)
+
+    @property
+    def dim(self):
+        if self.options["bounds"] is None:
+            raise Exception("Specify bounds for each dimension")
+        if self._dim is None:
+            self._dim = len(self.options["bounds"])
+        return self._dim
+
+    def create_data_dict(self):
+        self.data[self.key] = {"scores": None, "dist": None, "training_size": self.training_size,
+                               "bounds": self.options["bounds"], "seed": self.options["seed"],
+                               "N_samples": self.options["N_samples"], "gamma": self.gamma, "mean": None,
+                               "standard-deviation": None}
+
+    def update_data_dict(self, scored=False):
+        self.data[self.key].update({"mean": self.mean, "standard-deviation": self.sd})
+
+    def constructrng(self):
+        if self.options["seed"] is None:
+            print("There is no seed specified, so the generated results will be inconsistent")
+        self.rng = {"sampler": np.random.default_rng(self.options["seed"])}
+
+    def constructX(self, budget=10000):
+        """Candidate pool (data_gen.py:294-303): (10000,2) f64 integer lattice on [0,99]^2, x fastest."""
+        if self.options["bounds"] is None:
+            raise Exception("Neither the sample space was given and can not be constructed because bounds have not been specified.")
+        axes, _ = host.axis_grid(self.options["bounds"], budget, endpoint=False, dtype=np.float64)
+        self.X = np.stack(np.meshgrid(*axes), axis=-1).reshape(-1, self.dim)
+        self._X_dev = None
+
+    def _pool_device(self):
+        if self._X_dev is None or self._X_dev.shape[0] != self.X.shape[0]:
+            self._X_dev = torch.as_tensor(np.ascontiguousarray(self.X, dtype=np.float64), device=self.device)
+        return self._X_dev
+
+    # ------------------------------------------------------------------ generate / sample (data_gen.py:305-470)
+    def generate(self, method="subDPP"):
+        if self.options["time-debug"]:
+            self.start = time.perf_counter()
+        self.acquiredsets = []
+        self.key = None
+        if self.rng is None:
+            self.constructrng()
+        if self.X is None:
+            self.constructX()
+        if method == "subDPP" and self.training_size is None or self.gamma is None:      # precedence as data_gen.py:327
+            raise Exception("Training size or gamma has not been specified, so data can not be generated")
+        if method != "subDPP":
+            raise NotImplementedError("only the ranked-DPP ('subDPP') sampler is on the hot path")
+        return self.sub_dpp()
+
+    def sample(self, args=None, method="subDPP"):
+        if method != "subDPP":
+            raise NotImplementedError("only the ranked-DPP ('subDPP') sampler is on the hot path")
+        return self.sub_dpp_sample(args)
+
+    def iid_comb_locs(self, combination=None, sample_size=None):
+        if combination is None:
+            combination = self.X.shape[0], self.training_size
+        if sample_size is None:
+            sample_size = self.options["N_samples"]
+        return host.iid_comb_locs(combination[0], combination[1], sample_size, self.options["seed"])
+
+    def score_sets(self, idx: torch.Tensor, gamma=None) -> torch.Tensor:
+        """log det for index sets idx (N,k) int32 on device -> (N,) f64 on device."""
+        return ops.dpp_logdet_score(self._pool_device(), idx, self.gamma if gamma is None else gamma)
+
+    def sub_dpp(self):
+        if self.gamma is None and self.training_size == 10:
+            self.gamma = 1e-6
+        elif self.gamma is None:
+            raise Exception("self.gamma has not been fixed, look for a range of functional gammas using self.gammacalc")
+        if self.options["local_dir"]:
+            raise NotImplementedError("on-disk CSV mode is outside the hot path")
+        if self.options["time-debug"]:
+            t_setup = time.perf_counter()
+        elements = self.iid_comb_locs()
+        pos = self.combination_sampler.find_elms(self.X.shape[0], self.training_size, elements, device=self.device)
+        if bool((pos < 0).any()):
+            raise Exception("check previous")            # rank == C(n,k): the reference raises (Combination.py:150-153)
+        if self.options["time-debug"]:
+            torch.cuda.synchronize()
+            t_datagen = time.perf_counter()
+        pool = self._pool_device()
+        if self.training_size > 1:
+            logdet = self.score_sets(pos)
+            stats, z = ops.dpp_zscore(logdet)
+            z_sorted, ind = torch.sort(z, stable=True)       # ascending (score, set index): data_gen.py:409 made deterministic
+            dist = pool[pos.long()[ind]]
+            self.mean, self.sd = (float(v) for v in stats.cpu())
+            self._pos_sorted = pos[ind]
+            self.data[self.key].update({"scores": z_sorted.cpu().numpy(), "dist": dist.cpu().numpy()})
+            self.update_data_dict()
+        else:
+            self.data[self.key].update({"scores": "Can not be calculated for just a sample_set of size 1.",
+                                        "dist": pool[pos.long()].cpu().numpy()})
+        self.tracker["N_results"] += 1
+        if self.options["time-debug"]:
+            torch.cuda.synchronize()
+            t_score = time.perf_counter()
+            total = t_score - self.start
+            self.tracker["time-tracking"] = {"Total": total, "setting-up": (t_setup - self.start) / total,
+                                             "sampling": (t_datagen - t_setup) / total,
+                                             "scoring": (t_score - t_datagen) / total}
+            del self.start
+
+    @staticmethod
+    def _window(percentile, n):
+        """Rank window of one percentile (data_gen.py:445-450)."""
+        if 2.5 < percentile < 97.5:
+            return int((percentile - 2.5) / 100 * n), int(percentile / 100 * n)
+        if percentile > 97.5:
+            return int(95 / 100 * n), n
+        return 0, int(5 / 100 * n)
+
+    def _pick(self, percentile):
+        lo, hi = self._window(percentile, self.options["N_samples"])
+        possible = np.setdiff1d(list(range(lo, hi)), self.acquiredsets)
+        try:
+            loc = self.rng["sampler"].choice(list(possible), 1)[0]
+        except ValueError:
+            raise Exception("Constructed batch-DPP space exhausted above its {}th percentile. Re-generate the distribution "
+                            "or sample from a smaller percentile.".format(percentile))
+        self.acquiredsets.append(loc)
+        return loc
+
+    def sub_dpp_sample(self, percentiles):
+        try:
+            self.data[self.key]
+        except Exception:
+            raise Exception("Data needs to be generated first using the generator method")
+        if isinstance(percentiles, (list, np.ndarray)):
+            locs = [self._pick(p) for p in percentiles]
+            return self.data[self.key]["dist"][locs]
+        return self.data[self.key]["dist"][self._pick(percentiles)]
+
+    # ------------------------------------------------------------------ scoring API (data_gen.py:472-497)
+    def twoD_score(self, subset, gamma):
+        """Diversity score of one (k,2) point set: log det exp(-gamma * squared distances)."""
+        if not isinstance(subset, (list, np.ndarray)):
+            raise TypeError("A list or np.array was expected but a {} was entered as the subset".format(type(subset)))
+        first = subset[0][0]
+        if isinstance(first, (list, np.ndarray)):
+            raise ValueError("Elements of subset need to be a (numpy int,numpy int) but are ({},{})".format(type(first), type(first)))
+        if not isinstance(first, (np.int32, np.float64, np.float32, np.int64)):
+            raise TypeError("A list or np.array was expected but a {} was entered as the subset".format(type(subset)))
+        pts = torch.as_tensor(np.asarray(subset, dtype=np.float64), device=self.device)
+        k = pts.shape[0]
+        idx = torch.arange(k, dtype=torch.int32, device=self.device).reshape(1, k)
+        return float(ops.dpp_logdet_score(pts.contiguous(), idx, gamma)[0])
+
+    def compare_subDPP(self, resultkey, subset):
+        """Rank and z-score of an arbitrary set inside a stored distribution (data_gen.py:472-482)."""
+        d = self.data[resultkey]
+        score = self.twoD_score(subset, d["gamma"])
+        z = (score - d["mean"]) / d["standard-deviation"]
+        return int(np.sum(d["scores"] < z)), z
+
+    # ------------------------------------------------------------------ gamma selection (data_gen.py:758-842)
+    def gammacorrelation(self, g1, g2, min_samples):
+        import scipy.stats
+        self.options["N_samples"] = min_samples
+        self.options["parallel-process"] = False
+        self.gamma = 10 ** g1
+        self.generate()
+        score1 = self.data[self.key]["scores"]
+        self.gamma = 10 ** g2
+        s2 = self.score_sets(self._pos_sorted).cpu().numpy()
+        s2 = (s2 - s2.mean()) / np.std(s2)
+        x, y = np.argsort(score1), np.argsort(s2)
+        if np.isnan(s2).any():
+            np.random.shuffle(y)
+        return scipy.stats.linregress(x, y).rvalue
+
+    def gammacalc(self, grange=None, plot=False, annotations=False, min_samples=200):
+        if plot:
+            raise NotImplementedError("plotting is outside the hot path")
+        gamma_range = range(-12, 4) if grange is None else np.arange(*grange)
+        if self.gamma_correlation_dict is None:
+            self.gamma_correlation_dict = {}
+        m = np.zeros((len(gamma_range), len(gamma_range)))
+        for i, g1 in enumerate(gamma_range):
+            for j, g2 in enumerate(gamma_range):
+                try:
+                    m[i, j] = self.gamma_correlation_dict[g1][g2]
+                except KeyError:
+                    m[i, j] = self.gammacorrelation(g1, g2, min_samples)
+                    self.gamma_correlation_dict.setdefault(g1, {})[g2] = m[i, j]
+                    self.gamma_correlation_dict.setdefault(g2, {})[g1] = m[i, j]
+        np.fill_diagonal(m, 0)
+        pairs, min_cor = [], 0.95
+        while len(pairs) < 2:
+            rows, cols = np.where(m > min_cor)
+            pairs = np.stack([[gamma_range[i] for i in rows], [gamma_range[i] for i in cols]]).T
+            min_cor -= 0.05
+            if min_cor < 0.5:
+                print("Only Poorly coorelated gammas could be found for the given range of gamma(s).")
+                return
+        return pairs[np.abs([np.abs(p)[0] - np.abs(p)[1] for p in pairs]).argmax()]
+
+
+class random_data_generator:
+    """Uniformly random k-subsets of the pool. The reference's drivers call
+    ``data_gen.random_data_generator()`` (Experiment2.py:172) but the class is not defined in
+    Src/data_gen.py; this provides the obvious behaviour behind the same generate()/sample() calls."""
+
+    def __init__(self):
+        self.options = {"seed": None, "bounds": None, "N_samples": 10000}
+        self.training_size = None
+        self.X = None
+        self.acquiredsets = []
+        self.rng = None
+
+    def generate(self):
+        if self.X is None:
+            g = diverse_data_generator()
+            g.options["bounds"] = self.options["bounds"]
+            g.constructX()
+            self.X = g.X
+        self.rng = np.random.default_rng(self.options["seed"])
+
+    def sample(self, args=None):
+        if self.rng is None:
+            self.generate()
+        return self.X[self.rng.choice(self.X.shape[0], int(self.training_size), replace=False)]

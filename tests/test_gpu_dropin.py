@@ -1,0 +1,243 @@
+"""GPU: the reference-facing Python modules (objectives / data_gen / Combination / BO / Optimizers) called the
+way the reference's drivers call them (Scripts/Experiment2.py:160-226, Experiment3-2-3.py:194-224), checked
+against golden vectors from the reference's own code and against the oracle."""
+import math
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import AUTHOR_THETA_RAW
+from oracle import dpp as odpp
+from oracle import gp as ogp
+
+pytestmark = pytest.mark.gpu
+
+
+def test_objectives_wildcatwells_and_generate_cont(golden):
+    import objectives
+    g = golden("wildcat.npz")
+    o = objectives.objectives()
+    o.bounds = [(0, 100), (0, 100)]
+    o.seed = 0
+    o.args = {"N": 1, "Smoothness": 0.2, "rug_freq": 1, "rug_amp": 0.2}
+    X, surf = o.wildcatwells()
+    ref = g["surf_0"]
+    assert np.array_equal(X, g["X"]) and surf.dtype == np.float32 and surf.shape == (101, 101)
+    assert np.all(np.abs(surf - ref) <= np.spacing(np.abs(ref))) and np.mean(surf == ref) > 0.999
+    f = o.generate_cont()
+    q = np.array([[0.0, 0.0], [100.0, 100.0], [63.0, 56.0], [17.0, 99.0]])
+    v = f(q)
+    assert v.dtype == np.float64 and np.array_equal(v, surf[[0, 100, 56, 99], [0, 100, 63, 17]].astype(np.float64))
+    assert np.isnan(f(np.array([[100.5, 3.0]]))[0]) and np.isnan(f(np.array([[-0.1, 3.0]]))[0])
+    # off-node: main-diagonal triangulation of the unit cell (documented convention)
+    s = surf.astype(np.float64)
+    assert abs(f(np.array([[10.5, 20.25]]))[0] - (s[20, 10] + 0.5 * (s[20, 11] - s[20, 10]) + 0.25 * (s[21, 11] - s[20, 11]))) < 1e-12
+    assert abs(f(np.array([[10.25, 20.5]]))[0] - (s[20, 10] + 0.5 * (s[21, 10] - s[20, 10]) + 0.25 * (s[21, 11] - s[21, 10]))) < 1e-12
+    # the reference's Qhull interpolant at this point used one of the two diagonals; both bracket it
+    assert abs(f(np.array([[10.5, 20.25]]))[0] - g["cont_v"][0]) < 2.0
+    assert np.array_equal(f(torch.tensor([[56.0, 63.0]])), [100.0])        # torch input as in BO.py:104
+    from b200bo import ops
+    tab = f.grid_table(ops.Lattice(100, 100))
+    assert tab.dtype == torch.float32 and np.array_equal(tab.cpu().numpy(), surf[:100, :100].reshape(-1))
+    many = o.wildcatwells_batch([0, 3, 11, 5], [0.2, 0.8, 0.6, 0.4], [0.2, 0.4, 0.8, 0.6]).cpu().numpy()
+    for i in range(4):
+        assert np.mean(many[i] == g[f"surf_{i}"]) > 0.999
+
+
+def test_gpu_unrank_matches_reference(golden):
+    from Combination import combination_finder
+    cf = combination_finder()
+    rows = [r for r in golden("combinadics.json") if math.comb(r["n"], r["k"]) < 1 << 128]
+    groups = {}
+    for r in rows:
+        groups.setdefault((r["n"], r["k"]), []).append(r)
+    assert (10000, 10) in groups and (10000, 5) in groups and (100, 7) in groups
+    for (n, k), rs in groups.items():
+        out = cf.find_elms(n, k, [int(r["m"]) for r in rs]).cpu().numpy()
+        assert np.array_equal(out, np.array([r["set"] for r in rs])), (n, k)
+    big = [r for r in golden("combinadics.json") if math.comb(r["n"], r["k"]) >= 1 << 128]
+    assert big                                                               # (400, 50): host big-int path
+    out = cf.find_elms(big[0]["n"], big[0]["k"], [int(r["m"]) for r in big[:5]]).cpu().numpy()
+    assert np.array_equal(out, np.array([r["set"] for r in big[:5]]))
+    assert np.all(cf.find_elms(10000, 10, [math.comb(10000, 10)]).cpu().numpy() == -1)
+
+
+def test_data_gen_generate_matches_reference(golden):
+    """Experiment2.py:165-170 set-up; generate() / sample() / compare_subDPP vs the reference's run (seed 0)."""
+    import data_gen
+    g = golden("dpp.npz")
+    d = data_gen.diverse_data_generator()
+    d.options["bounds"] = [(0, 100), (0, 100)]
+    d.options["N_samples"] = 10000
+    d.gamma = 1e-5
+    d.options["seed"] = 0
+    d.training_size = 10
+    d.options["time-debug"] = True
+    d.generate()
+    key = d.key
+    assert len(key) == 8 and d.tracker["N_results"] == 1 and abs(sum(v for k, v in d.tracker["time-tracking"].items() if k != "Total") - 1) < 1e-6
+    mean_ref, sd_ref = g["gen_s0_mean_sd"]
+    assert abs(d.mean - mean_ref) < 1e-8 * abs(mean_ref) and abs(d.sd - sd_ref) < 1e-6 * sd_ref
+    assert d.data[key]["mean"] == d.mean and d.data[key]["standard-deviation"] == d.sd and d.data[key]["gamma"] == 1e-5
+    scores, dist = d.data[key]["scores"], d.data[key]["dist"]
+    assert scores.shape == (10000,) and dist.shape == (10000, 10, 2) and dist.dtype == np.float64
+    assert np.all(np.diff(scores) >= 0)
+    assert np.allclose(scores, g["gen_s0_scores"], rtol=0, atol=5e-5)        # z inherits conditioning-limited score error
+    same = np.all(dist.astype(np.int16) == g["gen_s0_dist"], axis=(1, 2))
+    assert same.mean() > 0.998                                               # rank swaps only among near-ties
+    s5 = d.sample(5)
+    s95 = d.sample(95)
+    assert list(d.acquiredsets) == list(g["gen_s0_acquired"])                # same ranks as the reference (462, 9409)
+    if same[d.acquiredsets[0]]:
+        assert np.array_equal(s5, g["gen_s0_sample5"])
+    if same[d.acquiredsets[1]]:
+        assert np.array_equal(s95, g["gen_s0_sample95"])
+    r, z = d.compare_subDPP(key, g["kat_pts"])
+    assert abs(r - g["gen_s0_compare"][0]) <= 2 and abs(z - g["gen_s0_compare"][1]) < 1e-6
+    for gamma, ref in zip(g["kat_gamma"], g["kat_score"]):
+        assert abs(d.twoD_score(g["kat_pts"], float(gamma)) - ref) <= odpp.cond_bound_rel(g["kat_pts"], float(gamma)) * abs(ref)
+    with pytest.raises(TypeError):
+        d.twoD_score("nope", 1e-5)
+    lst = d.sample([5, 95])
+    assert lst.shape == (2, 10, 2) and len(d.acquiredsets) == 4
+
+
+def _driver_setup(seed=0, sm=0.2, ra=0.2):
+    import data_gen
+    import objectives
+    synth_func = objectives.objectives()
+    synth_func.bounds = [(0, 100), (0, 100)]
+    synth_func.args = {"N": 1, "Smoothness": sm, "rug_freq": 1, "rug_amp": ra}
+    synth_func.seed = seed
+    f = synth_func.generate_cont()
+    synth_data = data_gen.diverse_data_generator()
+    synth_data.options["bounds"] = synth_func.bounds
+    synth_data.options["N_samples"] = 2000
+    synth_data.gamma = 1e-5
+    synth_data.options["seed"] = seed
+    synth_data.training_size = 10
+    synth_data.generate()
+    return synth_func, f, synth_data
+
+
+def test_optimizer_fixparam_like_experiment3(golden, lattice_grid):
+    """Experiment3-2-3.py:208-224 + singleopt: opt.train = sample(p); result = opt.optimize(f)."""
+    from Optimizers import optimizer
+    synth_func, f, synth_data = _driver_setup()
+    hp = golden("author_hyperparams.json")["0.2/0.2"]
+    for percentile in (5, 95):
+        BO_ = optimizer()
+        BO_.max_iter = 30
+        BO_.opt = "BO-fixparam"
+        BO_.tol = 0.1
+        BO_.minimize = synth_func.minstate
+        BO_.bounds = synth_func.bounds
+        BO_.datagenmodule = synth_data
+        BO_.paramset = hp
+        BO_.train = BO_.datagenmodule.sample(percentile)
+        random.seed(123)
+        res = BO_.optimize(f)
+        assert res.success and res._opt == 100 and res.minstate is False
+        assert res.yall.shape == (32,) and res.yall.dtype == np.float64
+        assert res.xall.shape == (res.nit, 2) and res.xall.dtype == np.float32
+        assert np.array_equal(res.traindata, BO_.train)
+        assert float(res.yopt) == res.yall[-1] and res.xopt.shape[1] == 2
+        assert np.array_equal(res.opt_gap, 100 - res.yall) and res.cum_opt_gap() >= 0
+        # same trial through the oracle: identical initial permutation, identical picks
+        random.seed(123)
+        picks = np.array(random.sample(range(10), 10))
+        X0 = BO_.train[picks].astype(np.float32).astype(np.float64)
+        surf = f.surf
+        y0 = surf[X0[:, 1].astype(int), X0[:, 0].astype(int)].astype(np.float64)
+        theta = ogp.raw_to_theta([hp[k][0] for k in ("likelihood.noise_covar.raw_noise", "mean_module.constant",
+                                                      "covar_module.raw_outputscale", "covar_module.base_kernel.raw_lengthscale")])
+        o = ogp.bo_loop(lattice_grid, surf[:100, :100].reshape(-1), X0, y0, 30, theta=theta, tol=0.1)
+        assert res.nit == o["nit"] and np.array_equal(res.yall, o["yall"])
+        assert np.array_equal(res.xall.astype(np.float64), o["xall"])
+
+
+def test_batched_fit_reaches_the_reference_optimum(golden, lattice_grid):
+    """K-C + batched L-BFGS from gpytorch's default start vs scipy L-BFGS-B on the oracle MLL
+    (the restatement of fit_gpytorch_model): same or better marginal likelihood."""
+    from b200bo import fit
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(0)
+    surfs = [golden("wildcat.npz")[f"surf_{i}"] for i in range(4)]
+    T, n_max = 24, 40
+    X = np.zeros((T, n_max, 2)); y = np.zeros((T, n_max)); n = np.zeros(T, dtype=np.int32)
+    for t in range(T):
+        n[t] = [10, 11, 15, 20, 30, 40][t % 6]
+        idx = rng.choice(10000, n[t], replace=False)
+        X[t, :n[t]] = lattice_grid[idx]
+        y[t, :n[t]] = surfs[t % 4][:100, :100].reshape(-1)[idx]
+    n[-1] = 0                                                     # inactive trial is skipped
+    fitter = fit.LBFGSFitter(T, dev)
+    theta = torch.zeros((T, 4), dtype=torch.float64, device=dev)
+    to = lambda a: torch.as_tensor(a, device=dev)
+    fitter.fit_into(to(X), to(y), to(n), 3, theta)
+    torch.cuda.synchronize()
+    raw = fitter.raw.cpu().numpy(); mll = fitter.mll.cpu().numpy(); iters = fitter.iters.cpu().numpy()
+    worse = 0
+    for t in range(T - 1):
+        v_here, g_here, _ = ogp.mll_value_grad(X[t, :n[t]], y[t, :n[t]], raw[t], 3)
+        assert abs(v_here - mll[t]) <= 1e-9 * abs(v_here)                   # reported optimum is consistent
+        assert raw[t, 0] >= 1e-4 - 1e-18                                   # bound respected
+        _, v_ref, res = ogp.fit_scipy(X[t, :n[t]], y[t, :n[t]], 3)
+        if mll[t] < v_ref - 1e-5 * abs(v_ref):
+            worse += 1
+        assert np.allclose(theta[t].cpu().numpy(), ogp.raw_to_theta(raw[t]), rtol=1e-12)
+        assert iters[t, 1] >= iters[t, 0] >= 1
+    assert worse <= 2, worse             # different optimisers may land in different local optima, rarely
+    assert torch.all(theta[-1] == 0)
+
+
+def test_boloop_with_fit_like_experiment2(golden):
+    """Experiment2.py:214-225 + singleopt (BO with per-iteration fitting)."""
+    from Optimizers import optimizer
+    synth_func, f, synth_data = _driver_setup(seed=1, sm=0.6, ra=0.4)
+    BO_ = optimizer()
+    BO_.max_iter = 15
+    BO_.opt = "BO"
+    BO_.tol = 0.1
+    BO_.minimize = synth_func.minstate
+    BO_.bounds = synth_func.bounds
+    BO_.datagenmodule = synth_data
+    BO_.train = BO_.datagenmodule.sample(95)
+    random.seed(7)
+    res = BO_.optimize(f)
+    assert res.success and res.yall.shape == (17,) and np.all(np.diff(res.yall) >= 0)
+    assert res.hpdata is not None
+    hp = res.hpdata.hyperparameters
+    assert set(hp) == {"likelihood.noise_covar.raw_noise", "mean_module.raw_constant", "covar_module.raw_outputscale",
+                       "covar_module.base_kernel.raw_lengthscale"}
+    assert all(len(v) == res.nit for v in hp.values())
+    assert np.all(hp["likelihood.noise_covar.raw_noise"] >= 1e-4 - 1e-18)
+    assert res.yall[-1] > res.yall[0] or res.nit < 15
+
+
+def test_single_call_entry_points(golden):
+    """BO.initialize_model / fit_gpytorch_model / ExpectedImprovement / optimize_acqf_and_get_observation used
+    directly, as Experiment3-2-1.py:66-72 does."""
+    import BO
+    synth_func, f, _ = _driver_setup(seed=0)
+    rng = np.random.default_rng(1)
+    X = rng.integers(0, 100, size=(12, 2)).astype(np.float64)
+    Y = f(X).astype(np.float32)
+    random.seed(0)
+    tx, ty, best = BO.generate_initial_data(X, Y, False, n=10)
+    mll, model = BO.initialize_model(tx, ty, nu=2.5)
+    BO.fit_gpytorch_model(mll)
+    raw = model.raw()
+    assert raw[0] >= 1e-4 and not np.allclose(raw, [2, 0, 0, 0])
+    v0 = ogp.mll_value_grad(tx.numpy().astype(np.float64), ty.numpy().reshape(-1).astype(np.float64), [2, 0, 0, 0], 3)[0]
+    v1 = ogp.mll_value_grad(tx.numpy().astype(np.float64), ty.numpy().reshape(-1).astype(np.float64), raw, 3)[0]
+    assert v1 > v0
+    EI = BO.ExpectedImprovement(model=model, best_f=best)
+    new_x, new_obj = BO.optimize_acqf_and_get_observation(EI, tx, f, len(tx), [(0, 100), (0, 100)])
+    assert new_x.shape == (1, 2) and new_obj.shape == (1, 1) and new_obj.dtype == torch.float32
+    grid = odpp.construct_pool()
+    idx, _, _ = ogp.grid_step(grid, tx.numpy().astype(np.float64), ty.numpy().reshape(-1).astype(np.float64), model.theta(), 3)
+    assert np.array_equal(new_x.numpy()[0].astype(np.float64), grid[idx])
+    assert new_obj.item() == f(grid[idx][None])[0].astype(np.float32)

@@ -1,0 +1,176 @@
+"""CPU: host-side logic of the product package and the C-ABI surface (no GPU needed: symbols only)."""
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import PKG, ROOT
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from b200bo import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "b200bo.h")).read()
+    declared = set(re.findall(r"\b(b200bo_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/b200bo.h but not exported"
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    assert "sm_100a" in _lib.version()
+    assert lib.b200bo_wfrag_doubles(8) == 2 * 32 and lib.b200bo_wfrag_doubles(110) == 14 * 15 * 32
+
+
+def test_built_for_sm_100a_only():
+    import subprocess
+    from b200bo import _lib
+    out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from b200bo import _lib, ops
+    with pytest.raises(_lib.B200boError):
+        ops.dpp_logdet_score(torch.zeros((4, 2), dtype=torch.float64), torch.zeros((1, 2), dtype=torch.int32), 0.1)
+    with pytest.raises(_lib.B200boError):
+        ops.gp_assemble_chol(torch.zeros((1, 4, 2), dtype=torch.float64), torch.zeros((1, 4), dtype=torch.float64),
+                             torch.ones(1, dtype=torch.int32), torch.ones((1, 4), dtype=torch.float64), 3)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), os.path.join(dirpath, f)
+
+
+def test_host_hash_and_simplex_setup(golden):
+    from b200bo import host
+    g = golden("simplex_noise.npz")
+    assert [host.rand_hash(int(v)) for v in g["hash_in"]] == [int(v) for v in g["hash_out"]]
+    for s in g["seeds"]:
+        h, vecs = host.simplex_setup(int(s))
+        assert h == int(g[f"hseed_{s}"][0]) and np.array_equal(np.array(vecs, dtype=np.int8), g[f"vecs_{s}"])
+    assert host.wildcat_peak(1) == (41.7022004702574, 32.664490177209615)
+
+
+def test_grids_match_reference(golden):
+    import data_gen
+    import objectives
+    o = objectives.objectives()
+    o.bounds = [(0, 100), (0, 100)]
+    assert np.array_equal(o.construct_X(), golden("wildcat.npz")["construct_X"])
+    X, NC = o.construct_X(with_noise_coords=True)
+    assert NC.shape == (101, 101, 2) and NC.dtype == np.float64 and NC[0, 1, 0] == 100 / 101
+    assert o.dim == 2
+    d = data_gen.diverse_data_generator()
+    with pytest.raises(Exception):
+        d.constructX()
+    d.options["bounds"] = [(0, 100), (0, 100)]
+    d.constructX()
+    assert np.array_equal(d.X, golden("dpp.npz")["pool"])
+    d.constructX(budget=40000)
+    assert d.X.shape == (40000, 2) and np.array_equal(d.X[:5], golden("dpp.npz")["pool40000_head"])
+
+
+def test_element_ranks_and_host_unrank(golden):
+    from b200bo import host
+    from Combination import combination_finder
+    g = golden("dpp.npz")
+    assert [str(e) for e in host.iid_comb_locs(10000, 10, 2000, 2)] == list(g["gen_s2_elements"])
+    cf = combination_finder()
+    for row in golden("combinadics.json"):
+        assert cf.find_elm(row["n"], row["k"], int(row["m"])) == row["set"]
+    assert cf.LargestV(8, 4, 7) == 5 and cf.reduced_comb(5, 2) == 10
+    with pytest.raises(Exception):
+        cf.find_elm(3, 5, 0)
+    with pytest.raises(Exception):
+        cf.find_elm(10000, 10, math.comb(10000, 10))
+
+
+def test_data_gen_api_contract():
+    import data_gen
+    d = data_gen.diverse_data_generator()
+    for attr in ("X", "gamma", "training_size", "options", "data", "key", "acquiredsets", "mean", "sd", "tracker", "rng"):
+        assert hasattr(d, attr)
+    with pytest.raises(Exception):
+        d.key = 5                                   # int seeds are rejected (data_gen.py:115-117)
+    d.training_size = 10.0
+    assert d.training_size == 10 and d.gamma_correlation_dict is None
+    d.options["bounds"] = [(0, 100), (0, 100)]
+    d.options["seed"] = 0
+    with pytest.raises(Exception):
+        d.generate()                                # gamma is None (data_gen.py:327)
+    with pytest.raises(Exception):
+        d.sample(5)                                 # nothing generated yet (data_gen.py:433-436)
+    assert d._window(5, 10000) == (250, 500) and d._window(95, 10000) == (9250, 9500)
+    assert d._window(99, 10000) == (9500, 10000) and d._window(1, 10000) == (0, 500)
+    r = data_gen.random_data_generator()
+    r.options["bounds"] = [(0, 100), (0, 100)]
+    r.options["seed"] = 1
+    r.training_size = 10
+    r.generate()
+    s = r.sample()
+    assert s.shape == (10, 2) and len({tuple(p) for p in s}) == 10
+
+
+def test_results_and_model_contract():
+    import BO
+    import results
+    from utils import cumoptgap
+    r = results.result_opt()
+    r._opt = 100
+    r.minstate = False
+    r.yall = np.array([50.0, 60.0, 90.0, 90.0])
+    assert np.array_equal(r.opt_gap, [50, 40, 10, 10])
+    assert r.cum_opt_gap() == np.trapezoid([40, 10, 10]) == cumoptgap(r.opt_gap[1:])
+    r.minstate = True
+    r._opt = 0
+    assert np.array_equal(r.opt_gap, r.yall)
+    mll, model = BO.initialize_model(np.zeros((3, 2)), np.zeros((3, 1)), nu=2.5)
+    names = [n for n, _ in model.named_parameters()]
+    assert names == list(BO.PARAM_NAMES)
+    assert [p.item() for _, p in model.named_parameters()] == [2.0, 0.0, 0.0, 0.0]     # gpytorch defaults
+    assert np.allclose(model.theta(), [2.0, 0.0, math.log(2), math.log(2)])
+    for _, p in model.named_parameters():
+        p.copy_(np.float64(1.5))
+    h = results.hp_result()
+    h.addhp(model)
+    assert h.hyperparameters[BO.PARAM_NAMES[3]] == [1.5]
+    assert BO.initialize_model(np.zeros((3, 2)), np.zeros((3, 1)), nu=1.5)[1].kernel_id == 2
+    assert BO.initialize_model(np.zeros((3, 2)), np.zeros((3, 1)), covar="rbf")[1].kernel_id == 0
+    th = BO._fixparam_to_theta({"likelihood.noise_covar.raw_noise": [0.5, 9], "mean_module.constant": [3.0],
+                                "covar_module.raw_outputscale": [30.0], "covar_module.base_kernel.raw_lengthscale": [0.0]})
+    assert np.allclose(th, [0.5, 3.0, 30.0, math.log(2)])
+    import random
+    random.seed(4)
+    tx, ty, best = BO.generate_initial_data(np.arange(24).reshape(12, 2), np.arange(12, dtype=np.float32), False, n=10)
+    assert tx.shape == (10, 2) and ty.shape == (10, 1) and best == ty.max()
+    lat = BO._lattice_for([(0, 100), (0, 100)])
+    assert (lat.Gx, lat.Gy, lat.h, lat.x0) == (100, 100, 1.0, 0.0)
+    lat = BO._lattice_for([(0, 100), (0, 100)], budget=40000)
+    assert (lat.Gx, lat.Gy, lat.h) == (200, 200, 0.5)
+
+
+def test_optimizer_facade_contract():
+    import Optimizers
+    o = Optimizers.optimizer()
+    assert o.max_iter == 100 and o.opt == "BO" and o.options["tol"] == 0.1 and o.options["nu"] == 2.5
+    assert o.optima == 100 and o.minimize is False
+    with pytest.raises(Exception):
+        o.optimize(lambda x: x, method="CG")
+
+
+def test_shard_ranges_cover_everything():
+    from b200bo import dist
+    for total in (0, 1, 7, 100000):
+        for world in (1, 2, 3, 8):
+            spans = [dist.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1

@@ -218,6 +218,23 @@ int main() {
   printf(", \"split_warps_ms\": %.4f, \"split_total_tflops\": %.3f", ms,
          (warps / 2 * ITER * 8 * 512 + nthreads / 2 * ITER * 8 * 2) / (ms * 1e-3) / 1e12);
 
+  // DMMA dependent-chain latency / ILP: W warps per SMSP (block = 128*W threads, 1 block per SM), A chains per warp
+  {
+    int cfgW[3] = {1, 2, 4};
+    for (int wi = 0; wi < 3; ++wi) {
+      int W = cfgW[wi];
+      int thr = 128 * W;
+      double wps = double(sms) * 4 * W;   // warps
+      float m1 = time_ms([&] { k_dmma<1><<<sms, thr>>>(out, 1.0000001, 1e-9); });
+      float m2 = time_ms([&] { k_dmma<2><<<sms, thr>>>(out, 1.0000001, 1e-9); });
+      float m4 = time_ms([&] { k_dmma<4><<<sms, thr>>>(out, 1.0000001, 1e-9); });
+      double clk = double(p.clockRate) * 1e3;
+      printf(", \"dmma_cyc_per_instr_W%d_A1\": %.2f, \"dmma_cyc_per_instr_W%d_A2\": %.2f, \"dmma_cyc_per_instr_W%d_A4\": %.2f",
+             W, m1 * 1e-3 * clk / (ITER * 1.0 * W), W, m2 * 1e-3 * clk / (ITER * 2.0 * W), W, m4 * 1e-3 * clk / (ITER * 4.0 * W));
+      (void)wps;
+    }
+  }
+
   const char* names[6] = {"exp", "sqrt", "erfc", "div", "rsqrt", "log"};
   float tms[6];
   tms[0] = time_ms([&] { k_trans<0><<<blocks, threads>>>(out, 0.3); });
