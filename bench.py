@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 BO engine — prints ONE JSON line (see the contract in the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (N > 1: launched by torchrun)
+    python bench.py --impl reference [--steps K] [--warmup W]      CPU arm: the oracle port on the host cores
+
+Workload (BASELINE.json configs[4] shard, the largest single-GPU configuration): 12 500 independent BO
+trials per GPU (100 000 / 8) on synthetic Wildcat Wells instances, 10 random initial lattice points each,
+fixed GP hyper-parameters (the authors' fitted values), Matérn-5/2, EI over the 100 x 100 candidate
+lattice, 100 iterations, tol disabled so every trial runs all iterations.  One step = one full batch.
+metric = BO iterations per second (trials x iterations / time), whole job over all GPUs.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "jmd-diversity-in-bayesian-optimization_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+AUTHOR_RAW = (0.0017619397258386016, 41.82688735961914, 190.43237411499024, 9.869425163269042)
+FAMILIES = [(s, r) for s in (0.2, 0.4, 0.6, 0.8) for r in (0.2, 0.4, 0.6, 0.8)]
+
+
+def softplus(v):
+    return v if v > 20.0 else float(np.log1p(np.exp(v)))
+
+
+THETA = (AUTHOR_RAW[0], AUTHOR_RAW[1], softplus(AUTHOR_RAW[2]), softplus(AUTHOR_RAW[3]))
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--trials-per-gpu", type=int, default=12500)
+    ap.add_argument("--iters", type=int, default=100)
+    ap.add_argument("--n0", type=int, default=10)
+    ap.add_argument("--surfaces", type=int, default=256)
+    ap.add_argument("--cpu-trials-per-core", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dpp", action="store_true")
+    return ap.parse_args()
+
+
+def init_sets(T, n0, seed):
+    """T random n0-subsets of the 10 000 lattice nodes (distinct inside a set), as flat indices."""
+    rng = np.random.default_rng(seed)
+    idx = rng.integers(0, 10000, size=(T, n0))
+    while True:
+        s = np.sort(idx, axis=1)
+        bad = np.nonzero((np.diff(s, axis=1) == 0).any(axis=1))[0]
+        if len(bad) == 0:
+            return idx
+        idx[bad] = rng.integers(0, 10000, size=(len(bad), n0))
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+
+def _cpu_worker(job):
+    seed, sm, ra, n0, iters, trial_seed = job
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle import gp as ogp, wildcat as owc, dpp as odpp
+    _, surf = owc.wildcatwells(seed, sm, ra)
+    grid = odpp.construct_pool()
+    obj = surf[:100, :100].reshape(-1)
+    idx = init_sets(1, n0, trial_seed)[0]
+    X0 = grid[idx]
+    y0 = obj[idx].astype(np.float64)
+    t0 = time.perf_counter()
+    out = ogp.bo_loop(grid, obj, X0, y0, iters, theta=THETA, kernel_id=3, tol=-1.0)
+    return out["nit"], time.perf_counter() - t0
+
+
+def cpu_sample(cores, trials_per_core, n0, iters):
+    """Oracle port of the same BO iteration on the host cores: one trial per process at a time (how the
+    reference fans trials out over ipyparallel engines, Scripts/Experiment2.py:110-141)."""
+    import multiprocessing as mp
+    jobs = [(i % 7, FAMILIES[i % 16][0], FAMILIES[i % 16][1], n0, iters, 1000 + i) for i in range(cores * trials_per_core)]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(0, 0.2, 0.2, n0, 2, 1)] * cores)       # import + warm-up, untimed
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+    its = sum(r[0] for r in res)
+    return its / wall, its, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals = []
+    for _ in range(args.warmup):
+        cpu_sample(cores, 1, args.n0, max(2, args.iters // 10))
+    t_all = 0.0
+    for _ in range(max(1, args.steps)):
+        v, its, wall = cpu_sample(cores, args.cpu_trials_per_core, args.n0, args.iters)
+        vals.append(v)
+        t_all += wall
+    value = float(np.mean(vals))
+    sample = f"{cores * args.cpu_trials_per_core} trials x {args.iters} iterations per step, one trial per core (numpy fp64 oracle port, 1 BLAS thread per process)"
+    line = {
+        "impl": "reference", "metric": "bo_iterations_per_s", "value": value, "unit": "BO iterations/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "BO iterations/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "BO iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "restated oracle (oracle/gp.py), not the botorch path: botorch/gpytorch are not installable here",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "BASELINE configs[4] shard: fixed-theta BO trials on 2-D Wildcat Wells, EI over the 100x100 lattice",
+            "trials_per_gpu": args.trials_per_gpu, "trials_total": args.trials_per_gpu * world, "iterations": args.iters,
+            "n_init": args.n0, "grid": "100x100", "kernel": "matern52", "acquisition": "EI", "tol": "disabled",
+            "hyperparameters": "fixed (authors' modes, smoothness 0.2 / ruggedness 0.2)", "surfaces": args.surfaces,
+            "l2_policy": "inputs larger than L2 (per-step working set ~0.7 GB of L^-1 fragments per GPU)",
+            "parallelism": f"trial-sharded x{world}, one final all-gather of gap curves"}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 8 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        pw = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+def run_b200(args):
+    import torch
+    from b200bo import dist, engine, ops
+    import objectives
+
+    rank, world, local = dist.init()
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    T, iters, n0, S = args.trials_per_gpu, args.iters, args.n0, args.surfaces
+    lat = ops.Lattice(100, 100)
+    grid = lat.points(dev)
+    G = lat.G
+
+    # ---- problem instances: S synthetic Wildcat Wells surfaces (K-E), objective table at the candidates
+    gen = objectives.objectives()
+    gen.device = str(dev)
+    seeds = [s // 16 for s in range(S)]
+    fam = [FAMILIES[s % 16] for s in range(S)]
+    surf = gen.wildcatwells_batch(seeds, [f[0] for f in fam], [f[1] for f in fam], device=dev)
+    obj_dev = surf[:, :100, :100].reshape(S, G).contiguous()
+    lo, hi = dist.shard_range(T * world, rank, world)
+    idx0 = init_sets(T, n0, 12345 + rank)
+    surf_id_h = ((np.arange(lo, hi)) % S).astype(np.int32)
+    grid_h = grid.cpu().numpy()
+    obj_h = obj_dev.cpu().numpy()
+    X0_h = torch.from_numpy(grid_h[idx0]).pin_memory()
+    y0_h = torch.from_numpy(obj_h[surf_id_h[:, None], idx0].astype(np.float64)).pin_memory()
+    sid_h = torch.from_numpy(surf_id_h).pin_memory()
+    objp_h = torch.from_numpy(obj_h).pin_memory()
+    X0_d, y0_d, sid_d = X0_h.to(dev), y0_h.to(dev), sid_h.to(dev)
+    theta = torch.tensor(THETA, dtype=torch.float64, device=dev)
+
+    bo = engine.BatchedBO(grid, obj_dev, sid_d, X0_d, y0_d, iters, theta=theta, kernel_id=ops.MATERN52, acq_id=ops.EI,
+                          tol=-1.0, lattice=lat, check_every=0)
+    yall_host = torch.empty((T, iters + 2), dtype=torch.float64).pin_memory()
+    nit_host = torch.empty(T, dtype=torch.int32).pin_memory()
+
+    def step_resident():
+        bo.reset(X0_d, y0_d)
+        res = bo.run()
+        curves = dist.gather_curves(res.yall)            # the path's only exchange (N > 1)
+        return res, curves
+
+    def step_e2e():
+        bo.obj.copy_(objp_h, non_blocking=True)          # host buffers -> device, every step
+        bo.reset(X0_h, y0_h, sid_h)
+        res = bo.run()
+        curves = dist.gather_curves(res.yall)
+        yall_host.copy_(res.yall, non_blocking=True)
+        nit_host.copy_(res.nit, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        return res, curves
+
+    peak = ops.fp64_fma_peak_tflops(dev)
+
+    def timed(fn, k):
+        dist.barrier(dev)
+        torch.cuda.synchronize(dev)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for _ in range(k):
+            last = fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        dist.barrier(dev)
+        return dist.max_over_ranks(e0.elapsed_time(e1), dev), last
+
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    bo.profile = []
+    ms_total, (res, curves) = timed(step_resident, args.steps)
+    prof = bo.profile
+    bo.profile = None
+    clocks = sampler.stop() if rank == 0 else None
+    launches = bo.launches * args.steps
+    nit_sum = int(res.nit.sum().item())
+    status_max = int(res.status.max().item())
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    # ---- roofline of the dominant kernel (fused grid posterior + EI + arg-max), measured in the timed steps
+    kb = [(n, e0.elapsed_time(e1)) for name, n, e0, e1 in prof if name == "grid_acq"]
+    ka = [(n, e0.elapsed_time(e1)) for name, n, e0, e1 in prof if name == "gp_chol"]
+    flops = sum(T * G * (n * n + 17 * n + 30) for n, _ in kb)
+    kb_ms = sum(ms for _, ms in kb)
+    ka_ms = sum(ms for _, ms in ka)
+    achieved = flops / (kb_ms * 1e-3) / 1e12 if kb_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_grid_acq_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "fp64", "kernel": "grid_acq_kernel<lattice> (K-B)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak if peak else None, "traffic": traffic,
+                "peak_source": "FP64 FMA issue rate measured in this run (b200bo_fp64_fma_probe); DMMA shares the pipe "
+                               "(profiles/fp64_peaks_r1.json). MEASURED_PEAKS.json holds HBM / bf16 only.",
+                "flops_model": "F_B = G (n^2 + 17 n + 30) per trial-iteration, exp/sqrt/erfc = 1 flop (SURVEY.md 8d)",
+                "kernel_share_of_step": kb_ms / ms_total if ms_total else None,
+                "gp_chol_share_of_step": ka_ms / ms_total if ms_total else None,
+                "launches_timed": len(kb)}
+
+    total_its = nit_sum * world            # every rank runs the same number of trial-iterations (tol disabled)
+    per_step_ms = ms_total / args.steps
+    value = total_its / (per_step_ms * 1e-3)
+    e2e_val = total_its / (ms_e2e / args.steps * 1e-3)
+    h2d = X0_h.numel() * 8 + y0_h.numel() * 8 + sid_h.numel() * 4 + objp_h.numel() * 4
+    d2h = yall_host.numel() * 8 + nit_host.numel() * 4
+
+    line = {"metric": "bo_iterations_per_s", "value": value, "unit": "BO iterations/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, world), "roofline": roofline,
+            "e2e": {"value": e2e_val, "unit": "BO iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "status_bits_seen": status_max,
+            "gathered_curves_shape": list(curves.shape)}
+
+    if rank == 0 and world == 1 and not args.no_dpp:
+        line["dpp"] = bench_dpp(dev)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v, its, wall = cpu_sample(cores, args.cpu_trials_per_core, n0, iters)
+        line["cpu_baseline"] = {"value": v, "unit": "BO iterations/s", "cores": cores, "kind": "port",
+                                "sample": f"{cores * args.cpu_trials_per_core} trials x {iters} iterations of the same workload "
+                                          f"({wall:.1f} s), one trial per core, numpy fp64 oracle port (oracle/gp.py)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as td
+        td.destroy_process_group()
+
+
+def bench_dpp(dev):
+    """Secondary metric of BASELINE.json: ranked-DPP sets scored per second (k = 10, gamma = 1e-5)."""
+    import torch
+    from b200bo import ops
+    lat = ops.Lattice(100, 100)
+    pool = lat.points(dev)
+    idx = torch.as_tensor(init_sets(100_000, 10, 7).astype(np.int32), device=dev)
+    big = idx.repeat(100, 1).contiguous()                                 # 1e7 sets for a throughput figure
+    out = {}
+    for name, t in (("n1e5", idx), ("n1e7", big)):
+        for _ in range(3):
+            ops.dpp_logdet_score(pool, t, 1e-5)
+        torch.cuda.synchronize(dev)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        reps = 5
+        for _ in range(reps):
+            ops.dpp_logdet_score(pool, t, 1e-5)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / reps
+        out[name] = {"sets": int(t.shape[0]), "ms": ms, "sets_per_s": t.shape[0] / (ms * 1e-3)}
+    # CPU: the oracle's twoD_score restatement (numpy slogdet), one core, bounded sample
+    from oracle import dpp as odpp
+    pool_h = pool.cpu().numpy()
+    sets = idx[:20000].cpu().numpy()
+    t0 = time.perf_counter()
+    for s in sets:
+        odpp.score_lu(pool_h[s], 1e-5)
+    dt = time.perf_counter() - t0
+    out["cpu_port"] = {"sets_per_s": len(sets) / dt, "cores": 1, "sample": f"{len(sets)} sets, numpy restatement of twoD_score"}
+    return out
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -92,6 +92,20 @@ class BatchedBO:
         self.launches = 0
         self.profile = None        # set to a list to collect (name, n, start_event, end_event) per launch
 
+    def reset(self, X0, y0, surf_id=None):
+        """Load a new batch of initial sets into the resident buffers (no allocation)."""
+        self.X.zero_()
+        self.y.zero_()
+        self.X[:, :self.n0].copy_(X0, non_blocking=True)
+        self.y[:, :self.n0].copy_(y0, non_blocking=True)
+        if surf_id is not None:
+            self.surf_id.copy_(surf_id, non_blocking=True)
+        self.n.fill_(self.n0)
+        self.status.zero_()
+        self.nit.zero_()
+        self.alpha.zero_()
+        self.launches = 0
+
     def _timed(self, name, n, fn):
         if self.profile is None:
             return fn()

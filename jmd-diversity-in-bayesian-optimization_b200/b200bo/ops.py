@@ -161,12 +161,12 @@ def wildcat_eval(surf: torch.Tensor, xy: torch.Tensor, surf_id=None) -> torch.Te
     return out
 
 
-def fp64_fma_peak_tflops(device=None, reps=5) -> float:
+def fp64_fma_peak_tflops(device=None, reps=8) -> float:
     """Measured FP64 FMA throughput of the current GPU in TFLOP/s (best of ``reps``, CUDA events)."""
     lib = _lib.load()
     dev = torch.device(device or "cuda")
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    blocks, iters = sms * 8, 4096
+    blocks, iters = sms * 8, 32768
     out = torch.empty(blocks * 256, dtype=torch.float64, device=dev)
     best = 0.0
     for r in range(reps + 2):

@@ -20,6 +20,7 @@
 // bytes (L2-resident, shared by all trials).
 #include "common.cuh"
 #include <limits.h>
+#include <stdlib.h>
 
 namespace b200bo {
 
@@ -31,6 +32,63 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
+
+
+// V = L^-1 K* on the FP64 MMA path. Row blocks (8 rows of L^-1) are processed in groups of up to CH:
+// one accumulator chain per row block, so a warp has CH independent DMMA chains in flight (a single
+// chain is latency bound: 29 cycles per dependent DMMA against a 16-cycle issue interval). Row block
+// I needs the k-blocks J <= 2I+1 (lower triangle); the group issues J ascending and a chain simply
+// stops when its staircase ends. I and J are compile-time so kval[] stays in registers.
+template <int I, int NB, int NT, int NKV>
+__device__ __forceinline__ void mma_group(const double* __restrict__ wsm, int lane, const double (&kval)[NT][NKV],
+                                          double (&ss)[NT][2]) {
+  double acc[NB][NT][2];
+#pragma unroll
+  for (int b = 0; b < NB; ++b)
+#pragma unroll
+    for (int tt = 0; tt < NT; ++tt) { acc[b][tt][0] = 0.0; acc[b][tt][1] = 0.0; }
+#pragma unroll
+  for (int J = 0; J <= 2 * (I + NB - 1) + 1; ++J) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+      if (J <= 2 * (I + b) + 1) {
+        // one shared-memory fragment of L^-1 feeds NT column tiles (halves LSU traffic per DMMA at NT = 2)
+        const double a = wsm[(size_t)((I + b) * (I + b + 1) + J) * 32 + lane];
+#pragma unroll
+        for (int tt = 0; tt < NT; ++tt) dmma_m8n8k4(acc[b][tt][0], acc[b][tt][1], a, kval[tt][J]);
+      }
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b)
+#pragma unroll
+    for (int tt = 0; tt < NT; ++tt) {
+      ss[tt][0] = fma(acc[b][tt][0], acc[b][tt][0], ss[tt][0]);
+      ss[tt][1] = fma(acc[b][tt][1], acc[b][tt][1], ss[tt][1]);
+    }
+}
+
+template <int I, int CH, int NI_MAX, bool END = (I >= NI_MAX)>
+struct MmaGroups {
+  template <int NT, int NKV>
+  static __device__ __forceinline__ void run(const double* __restrict__ wsm, int lane, int nI,
+                                             const double (&kval)[NT][NKV], double (&ss)[NT][2]) {
+    if (I < nI) {                       // uniform
+      const int nb = nI - I;
+      if (nb >= CH) mma_group<I, CH>(wsm, lane, kval, ss);
+      else if (CH > 3 && nb == 3) mma_group<I, (CH > 3 ? 3 : 1)>(wsm, lane, kval, ss);
+      else if (CH > 2 && nb == 2) mma_group<I, (CH > 2 ? 2 : 1)>(wsm, lane, kval, ss);
+      else mma_group<I, 1>(wsm, lane, kval, ss);
+      MmaGroups<I + CH, CH, NI_MAX>::run(wsm, lane, nI, kval, ss);
+    }
+  }
+};
+
+template <int I, int CH, int NI_MAX>
+struct MmaGroups<I, CH, NI_MAX, true> {
+  template <int NT, int NKV>
+  static __device__ __forceinline__ void run(const double* __restrict__, int, int, const double (&)[NT][NKV],
+                                             double (&)[NT][2]) {}
+};
 
 struct GridAcqParams {
   const double2* grid;      // (G) candidates
@@ -65,8 +123,8 @@ struct GridAcqParams {
   const int32_t* ktab_id;   // (T) table slot per trial, or null = slot 0
 };
 
-template <int KID, int NI_MAX, bool LATTICE>
-__global__ void __launch_bounds__(GA_THREADS, (NI_MAX <= 8 ? 4 : 3))
+template <int KID, int NI_MAX, bool LATTICE, int CH, int MINB, int NT>
+__global__ void __launch_bounds__(GA_THREADS, MINB)
 grid_acq_kernel(const GridAcqParams p) {
   extern __shared__ double sm[];
   const int t = blockIdx.x / p.chunks;
@@ -136,102 +194,90 @@ grid_acq_kernel(const GridAcqParams p) {
     double my_ss = 0.0, my_mu = 0.0;
     int my_masked = 0;
 #pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
-      const int gb = min(base + 8 * q + bcol, p.G - 1);
-      double kval[2 * NI_MAX];
-      double mu_part = 0.0;
-      int masked = 0;
-      if (LATTICE) {
-        const int gyi = gb / p.Gx, gxi = gb - gyi * p.Gx;
-        // chunks of 8 k-blocks: 8 index computations, then 8 independent table loads in flight,
-        // then 8 FMAs — one uniform branch per chunk instead of one per look-up
+    for (int q = 0; q < 4; q += NT) {
+      double kval[NT][2 * NI_MAX];
+      double mu_part[NT];
+      int masked[NT];
 #pragma unroll
-        for (int Jb = 0; Jb < 2 * NI_MAX; Jb += 8) {
-          if (Jb < nJ) {
-            int kix[8];
+      for (int tt = 0; tt < NT; ++tt) {
+        const int gb = min(base + 8 * (q + tt) + bcol, p.G - 1);
+        mu_part[tt] = 0.0;
+        masked[tt] = 0;
+        if (LATTICE) {
+          const int gyi = gb / p.Gx, gxi = gb - gyi * p.Gx;
+          // chunks of 8 k-blocks: 8 index computations, then 8 independent table loads in flight,
+          // then 8 FMAs — one uniform branch per chunk instead of one per look-up
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int j = 4 * (Jb + u) + jrow;
-              const int pk = xyi[j];
-              const int dxi = abs(gxi - (pk & 0xffff)), dyi = abs(gyi - (pk >> 16));
-              kix[u] = dyi * p.Gx + dxi;
-              masked |= (kix[u] == 0 && j < n) ? 1 : 0;     // dxi < Gx, so 0 <=> dxi == dyi == 0
+          for (int Jb = 0; Jb < 2 * NI_MAX; Jb += 8) {
+            if (Jb < nJ) {
+              int kix[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int j = 4 * (Jb + u) + jrow;
+                const int pk = xyi[j];
+                const int dxi = abs(gxi - (pk & 0xffff)), dyi = abs(gyi - (pk >> 16));
+                kix[u] = dyi * p.Gx + dxi;
+                masked[tt] |= (kix[u] == 0 && j < n) ? 1 : 0;     // dxi < Gx, so 0 <=> dxi == dyi == 0
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) kval[tt][Jb + u] = __ldg(tab + kix[u]);
+              // padded observations (j >= n) hit columns of L^-1 that are zero and alpha = 0: any finite
+              // table value is harmless there
+#pragma unroll
+              for (int u = 0; u < 8; ++u) mu_part[tt] = fma(kval[tt][Jb + u], al[4 * (Jb + u) + jrow], mu_part[tt]);
             }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) kval[Jb + u] = __ldg(tab + kix[u]);
-            // padded observations (j >= n) hit columns of L^-1 that are zero and alpha = 0: any finite
-            // table value is harmless there
-#pragma unroll
-            for (int u = 0; u < 8; ++u) mu_part = fma(kval[Jb + u], al[4 * (Jb + u) + jrow], mu_part);
           }
-        }
-      } else {
-        const double2 gp = __ldg(&p.grid[gb]);
+        } else {
+          const double2 gp = __ldg(&p.grid[gb]);
 #pragma unroll
-        for (int J = 0; J < 2 * NI_MAX; ++J) {
-          kval[J] = 0.0;
-          if (J < nJ) {
-            const int j = 4 * J + jrow;
-            const double dx = gp.x - xs[j], dy = gp.y - ys[j];
-            const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-            double kv = kernel_from_r2<KID>(r2, sc, ell, kp.a_scale);
-            const bool valid = j < n;
-            kv = valid ? kv : 0.0;
-            masked |= (valid && r2 == 0.0) ? 1 : 0;
-            kval[J] = kv;
-            mu_part = fma(kv, al[j], mu_part);
+          for (int J = 0; J < 2 * NI_MAX; ++J) {
+            kval[tt][J] = 0.0;
+            if (J < nJ) {
+              const int j = 4 * J + jrow;
+              const double dx = gp.x - xs[j], dy = gp.y - ys[j];
+              const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+              double kv = kernel_from_r2<KID>(r2, sc, ell, kp.a_scale);
+              const bool valid = j < n;
+              kv = valid ? kv : 0.0;
+              masked[tt] |= (valid && r2 == 0.0) ? 1 : 0;
+              kval[tt][J] = kv;
+              mu_part[tt] = fma(kv, al[j], mu_part[tt]);
+            }
           }
         }
       }
       // V = L^-1 K* on the FP64 MMA path; accumulate squared entries per C column
-      double ss0 = 0.0, ss1 = 0.0;
+      double ss[NT][2];
 #pragma unroll
-      for (int I = 0; I < NI_MAX; I += 2) {
-        if (I < nI) {
-          // two independent accumulator chains (row blocks I and I+1) keep the FP64 MMA pipe fed
-          double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-          const double* w0 = wsm + (size_t)(I * (I + 1)) * 32 + lane;
-          const double* w1 = wsm + (size_t)((I + 1) * (I + 2)) * 32 + lane;
-          if (I + 1 < nI) {
+      for (int tt = 0; tt < NT; ++tt) { ss[tt][0] = 0.0; ss[tt][1] = 0.0; }
+      MmaGroups<0, CH, NI_MAX>::run(wsm, lane, nI, kval, ss);
 #pragma unroll
-            for (int J = 0; J <= 2 * I + 1; ++J) {
-              dmma_m8n8k4(a0, a1, w0[J * 32], kval[J]);
-              dmma_m8n8k4(b0, b1, w1[J * 32], kval[J]);
-            }
-            dmma_m8n8k4(b0, b1, w1[(2 * I + 2) * 32], kval[2 * I + 2]);
-            dmma_m8n8k4(b0, b1, w1[(2 * I + 3) * 32], kval[2 * I + 3]);
-            ss0 = fma(b0, b0, ss0);
-            ss1 = fma(b1, b1, ss1);
-          } else {
+      for (int tt = 0; tt < NT; ++tt) {
+        double ss0 = ss[tt][0], ss1 = ss[tt][1], mp = mu_part[tt];
+        int mk = masked[tt];
+        // rows live in lane>>2: reduce over xor 4, 8, 16
 #pragma unroll
-            for (int J = 0; J <= 2 * I + 1; ++J) dmma_m8n8k4(a0, a1, w0[J * 32], kval[J]);
-          }
-          ss0 = fma(a0, a0, ss0);
-          ss1 = fma(a1, a1, ss1);
+        for (int o = 4; o < 32; o <<= 1) {
+          ss0 += __shfl_xor_sync(0xffffffffu, ss0, o);
+          ss1 += __shfl_xor_sync(0xffffffffu, ss1, o);
         }
-      }
-      // rows live in lane>>2: reduce over xor 4, 8, 16
+        // k-rows live in lane&3: reduce over xor 1, 2
 #pragma unroll
-      for (int o = 4; o < 32; o <<= 1) {
-        ss0 += __shfl_xor_sync(0xffffffffu, ss0, o);
-        ss1 += __shfl_xor_sync(0xffffffffu, ss1, o);
-      }
-      // k-rows live in lane&3: reduce over xor 1, 2
-#pragma unroll
-      for (int o = 1; o < 4; o <<= 1) {
-        mu_part += __shfl_xor_sync(0xffffffffu, mu_part, o);
-        masked |= __shfl_xor_sync(0xffffffffu, masked, o);
-      }
-      // hand column cc = lane&7 of this tile to lane 8q + cc
-      const int cc = lane & 7;
-      const double t0 = __shfl_sync(0xffffffffu, ss0, cc >> 1);
-      const double t1 = __shfl_sync(0xffffffffu, ss1, cc >> 1);
-      const double tm = __shfl_sync(0xffffffffu, mu_part, cc * 4);
-      const int tk = __shfl_sync(0xffffffffu, masked, cc * 4);
-      if ((lane >> 3) == q) {
-        my_ss = (cc & 1) ? t1 : t0;
-        my_mu = tm;
-        my_masked = tk;
+        for (int o = 1; o < 4; o <<= 1) {
+          mp += __shfl_xor_sync(0xffffffffu, mp, o);
+          mk |= __shfl_xor_sync(0xffffffffu, mk, o);
+        }
+        // hand column cc = lane&7 of this tile to lane 8(q+tt) + cc
+        const int cc = lane & 7;
+        const double t0 = __shfl_sync(0xffffffffu, ss0, cc >> 1);
+        const double t1 = __shfl_sync(0xffffffffu, ss1, cc >> 1);
+        const double tm = __shfl_sync(0xffffffffu, mp, cc * 4);
+        const int tk = __shfl_sync(0xffffffffu, mk, cc * 4);
+        if ((lane >> 3) == q + tt) {
+          my_ss = (cc & 1) ? t1 : t0;
+          my_mu = tm;
+          my_masked = tk;
+        }
       }
     }
     const int g = base + lane;
@@ -268,6 +314,219 @@ grid_acq_kernel(const GridAcqParams p) {
     p.part_val[(size_t)t * p.chunks + chunk] = bv;
     p.part_idx[(size_t)t * p.chunks + chunk] = bi;
     if (red_flag && p.status) atomicOr(&p.status[t], red_flag);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Lattice K-B, k-outer schedule (the production path for lattice candidates).
+//
+// Same math and fragment layout as grid_acq_kernel, different loop order: the k-blocks J run in the
+// outer loop and every row block I >= J/2 accumulates into its own register pair, so
+//   * only ONE cross-covariance fragment value is live at a time (no kval[] array): ~100 registers
+//     instead of ~165, i.e. 16-20 resident warps per SM instead of 12;
+//   * for a fixed J the DMMAs of different row blocks are independent: up to NI chains in flight;
+//   * the table look-up of k-block J+2 is issued while k-blocks J, J+1 run on the MMA pipe.
+// NI = ceil(n_cap / 8) is a template parameter so that all accumulators and the triangular loop
+// bounds are compile-time; trials with fewer row blocks (ragged batches) take the predicated body.
+template <int NI, bool EXACT>
+__device__ __forceinline__ void lattice_tile(const double* __restrict__ wsm, const int* __restrict__ xyi,
+                                             const double* __restrict__ al, const double* __restrict__ tab, int Gx,
+                                             int gxi, int gyi, int jrow, int lane, int n, int nI, double& ss0,
+                                             double& ss1, double& mu_part, int& masked) {
+  constexpr int NJ = 2 * NI;
+  double acc[NI][2];
+#pragma unroll
+  for (int I = 0; I < NI; ++I) { acc[I][0] = 0.0; acc[I][1] = 0.0; }
+  auto index_of = [&](int J) {
+    const int pk = xyi[4 * J + jrow];
+    const int dxi = abs(gxi - (pk & 0xffff)), dyi = abs(gyi - (pk >> 16));
+    return dyi * Gx + dxi;
+  };
+  // software pipeline: table values two k-blocks ahead
+  int ix0 = index_of(0), ix1 = index_of(1);
+  double kv0 = __ldg(tab + ix0), kv1 = __ldg(tab + ix1);
+  mu_part = 0.0;
+  masked = 0;
+#pragma unroll
+  for (int J = 0; J < NJ; ++J) {
+    if (!EXACT && J >= 2 * nI) break;                      // uniform
+    const double kv = kv0;
+    const int ix = ix0;
+    kv0 = kv1; ix0 = ix1;
+    if (J + 2 < NJ && (EXACT || J + 2 < 2 * nI)) {
+      ix1 = index_of(J + 2);
+      kv1 = __ldg(tab + ix1);
+    }
+    // padded observations (j >= n) meet zero columns of L^-1 and alpha = 0: any finite value is harmless
+    masked |= (ix == 0 && 4 * J + jrow < n) ? 1 : 0;       // dxi < Gx, so index 0 <=> the observed point itself
+    mu_part = fma(kv, al[4 * J + jrow], mu_part);
+#pragma unroll
+    for (int I = J / 2; I < NI; ++I) {
+      if (EXACT || I < nI)
+        dmma_m8n8k4(acc[I][0], acc[I][1], wsm[(size_t)(I * (I + 1) + J) * 32 + lane], kv);
+    }
+  }
+  ss0 = 0.0;
+  ss1 = 0.0;
+#pragma unroll
+  for (int I = 0; I < NI; ++I) {
+    ss0 = fma(acc[I][0], acc[I][0], ss0);
+    ss1 = fma(acc[I][1], acc[I][1], ss1);
+  }
+}
+
+template <int NI>
+__global__ void __launch_bounds__(GA_THREADS, (NI <= 8 ? 5 : 4))
+grid_acq_lattice_kernel(const GridAcqParams p) {
+  extern __shared__ double sm[];
+  const int t = blockIdx.x / p.chunks;
+  const int chunk = blockIdx.x - t * p.chunks;
+  const int n = p.n[t];
+  if (n <= 0) return;                     // finished / inactive trial (uniform per CTA)
+  if (n > p.n_cap || n > 8 * NI) {        // n_hint too small: report, do not touch memory
+    if (threadIdx.x == 0) {
+      p.part_val[(size_t)t * p.chunks + chunk] = -INFINITY;
+      p.part_idx[(size_t)t * p.chunks + chunk] = INT_MAX;
+      if (p.status) atomicOr(&p.status[t], B200BO_ST_ALL_MASKED);
+    }
+    return;
+  }
+  const int nI = (n + 7) >> 3;
+  const int npad = 8 * NI;                // look-ups may run one k-block pair ahead of nI: stage the full template size
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nblk = nI * (nI + 1);
+  double* wsm = sm;                       // NI (NI + 1) * 32
+  double* al = sm + (size_t)NI * (NI + 1) * 32;
+  int* xyi = reinterpret_cast<int*>(al + npad);
+  __shared__ double red_val[GA_WARPS];
+  __shared__ int red_idx[GA_WARPS];
+  __shared__ int red_flag;
+  {
+    const double2* src = reinterpret_cast<const double2*>(p.wfrag + (size_t)t * p.wstride);
+    double2* dst = reinterpret_cast<double2*>(wsm);
+    for (int e = threadIdx.x; e < nblk * 16; e += GA_THREADS) dst[e] = src[e];
+    for (int j = threadIdx.x; j < npad; j += GA_THREADS) {
+      const bool v = j < n;
+      const double x = v ? p.X[((size_t)t * p.n_max + j) * 2] : p.x0;
+      const double y = v ? p.X[((size_t)t * p.n_max + j) * 2 + 1] : p.y0;
+      al[j] = v ? p.alpha[(size_t)t * p.n_max + j] : 0.0;
+      const double fx = rint((x - p.x0) / p.h), fy = rint((y - p.y0) / p.h);
+      const bool on = (p.x0 + p.h * fx == x) && (p.y0 + p.h * fy == y) && fx >= 0.0 && fy >= 0.0 &&
+                      fx < (double)p.Gx && fy < (double)p.Gy;
+      xyi[j] = on ? ((int)fx | ((int)fy << 16)) : 0;
+      if (v && !on && p.status) atomicOr(&p.status[t], B200BO_ST_OFF_LATTICE);
+    }
+    if (threadIdx.x == 0) red_flag = 0;
+  }
+  const double* tab = p.ktab + (size_t)(p.ktab_id ? p.ktab_id[t] : 0) * p.Gx * p.Gy;
+  const double cst = p.theta[(size_t)t * 4 + 1];
+  const double sc = p.theta[(size_t)t * 4 + 2];
+  const double best_f = p.best_f[t];
+  __syncthreads();
+
+  const int col0 = chunk * p.cols_per_cta;
+  const int col_end = min(p.G, col0 + p.cols_per_cta);
+  const int jrow = lane & 3, bcol = lane >> 2;
+  double best_v = -INFINITY;
+  int best_i = INT_MAX;
+  int flags = 0;
+
+  for (int base = col0 + warp * 32; base < col_end; base += GA_WARPS * 32) {
+    double my_ss = 0.0, my_mu = 0.0;
+    int my_masked = 0;
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+      const int gb = min(base + 8 * q + bcol, p.G - 1);
+      const int gyi = gb / p.Gx, gxi = gb - gyi * p.Gx;
+      double ss0, ss1, mp;
+      int mk;
+      if (nI == NI) lattice_tile<NI, true>(wsm, xyi, al, tab, p.Gx, gxi, gyi, jrow, lane, n, nI, ss0, ss1, mp, mk);
+      else lattice_tile<NI, false>(wsm, xyi, al, tab, p.Gx, gxi, gyi, jrow, lane, n, nI, ss0, ss1, mp, mk);
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {                  // rows live in lane>>2
+        ss0 += __shfl_xor_sync(0xffffffffu, ss0, o);
+        ss1 += __shfl_xor_sync(0xffffffffu, ss1, o);
+      }
+#pragma unroll
+      for (int o = 1; o < 4; o <<= 1) {                   // k-rows live in lane&3
+        mp += __shfl_xor_sync(0xffffffffu, mp, o);
+        mk |= __shfl_xor_sync(0xffffffffu, mk, o);
+      }
+      const int cc = lane & 7;                            // hand column cc of this tile to lane 8q + cc
+      const double t0 = __shfl_sync(0xffffffffu, ss0, cc >> 1);
+      const double t1 = __shfl_sync(0xffffffffu, ss1, cc >> 1);
+      const double tm = __shfl_sync(0xffffffffu, mp, cc * 4);
+      const int tk = __shfl_sync(0xffffffffu, mk, cc * 4);
+      if ((lane >> 3) == q) {
+        my_ss = (cc & 1) ? t1 : t0;
+        my_mu = tm;
+        my_masked = tk;
+      }
+    }
+    const int g = base + lane;
+    if (g < col_end) {
+      const double mu = cst + my_mu;
+      const double var = sc - my_ss;
+      double a;
+      if (p.acq_id == B200BO_ACQ_UCB) a = acquisition<B200BO_ACQ_UCB>(mu, var, best_f, p.acq_param, p.var_floor);
+      else if (p.acq_id == B200BO_ACQ_PI) a = acquisition<B200BO_ACQ_PI>(mu, var, best_f, p.acq_param, p.var_floor);
+      else a = acquisition<B200BO_ACQ_EI>(mu, var, best_f, p.acq_param, p.var_floor);
+      if (p.mu_out) p.mu_out[(size_t)t * p.G + g] = mu;
+      if (p.var_out) p.var_out[(size_t)t * p.G + g] = var;
+      if (p.acq_out) p.acq_out[(size_t)t * p.G + g] = a;
+      const bool m = (p.mask_observed && my_masked) || (p.extra_mask && p.extra_mask[g]);
+      if (!m) {
+        if (isnan(a) || a == INFINITY) flags |= B200BO_ST_NONFINITE;
+        if (!isnan(a) && better(a, g, best_v, best_i)) { best_v = a; best_i = g; }
+      }
+    }
+  }
+  warp_argmax(best_v, best_i);
+  flags = __reduce_or_sync(0xffffffffu, flags);
+  if (lane == 0) {
+    red_val[warp] = best_v;
+    red_idx[warp] = best_i;
+    if (flags) atomicOr(&red_flag, flags);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double bv = red_val[0];
+    int bi = red_idx[0];
+    for (int w = 1; w < GA_WARPS; ++w)
+      if (better(red_val[w], red_idx[w], bv, bi)) { bv = red_val[w]; bi = red_idx[w]; }
+    p.part_val[(size_t)t * p.chunks + chunk] = bv;
+    p.part_idx[(size_t)t * p.chunks + chunk] = bi;
+    if (red_flag && p.status) atomicOr(&p.status[t], red_flag);
+  }
+}
+
+template <int NI>
+static int launch_lattice(const GridAcqParams& p, int T, cudaStream_t st) {
+  size_t smem = ((size_t)NI * (NI + 1) * 32 + 8 * (size_t)NI) * sizeof(double) + 8 * (size_t)NI * sizeof(int);
+  cudaError_t e = cudaFuncSetAttribute(grid_acq_lattice_kernel<NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_status(e, "grid_posterior_acq_argmax_lattice: smem attribute");
+  grid_acq_lattice_kernel<NI><<<(unsigned)((size_t)T * p.chunks), GA_THREADS, smem, st>>>(p);
+  return 0;
+}
+
+static int dispatch_lattice(const GridAcqParams& p, int T, cudaStream_t st) {
+  switch ((p.n_cap + 7) / 8) {
+    case 1: return launch_lattice<1>(p, T, st);
+    case 2: return launch_lattice<2>(p, T, st);
+    case 3: return launch_lattice<3>(p, T, st);
+    case 4: return launch_lattice<4>(p, T, st);
+    case 5: return launch_lattice<5>(p, T, st);
+    case 6: return launch_lattice<6>(p, T, st);
+    case 7: return launch_lattice<7>(p, T, st);
+    case 8: return launch_lattice<8>(p, T, st);
+    case 9: return launch_lattice<9>(p, T, st);
+    case 10: return launch_lattice<10>(p, T, st);
+    case 11: return launch_lattice<11>(p, T, st);
+    case 12: return launch_lattice<12>(p, T, st);
+    case 13: return launch_lattice<13>(p, T, st);
+    case 14: return launch_lattice<14>(p, T, st);
+    case 15: return launch_lattice<15>(p, T, st);
+    default: return launch_lattice<16>(p, T, st);
   }
 }
 
@@ -309,18 +568,32 @@ inline size_t grid_acq_smem(int nI) {
   return ((size_t)nI * (nI + 1) * 32 + 3 * npad) * sizeof(double) + npad * sizeof(int);
 }
 
-template <int KID, int NI_MAX, bool LATTICE>
-static int launch_grid_acq(const GridAcqParams& p, int T, cudaStream_t st) {
+template <int KID, int NI_MAX, bool LATTICE, int CH, int MINB, int NT>
+static int launch_grid_acq_v(const GridAcqParams& p, int T, cudaStream_t st) {
   size_t smem = grid_acq_smem(NI_MAX);
-  cudaError_t e = cudaFuncSetAttribute(grid_acq_kernel<KID, NI_MAX, LATTICE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(grid_acq_kernel<KID, NI_MAX, LATTICE, CH, MINB, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e, "grid_posterior_acq_argmax: smem attribute");
   // dynamic smem sized by the largest n actually possible in this instantiation would waste
   // occupancy for small n; size it by n_max rounded to the tile instead.
   int nIa = (p.n_cap + 7) / 8;
   if (nIa > NI_MAX) nIa = NI_MAX;
   smem = grid_acq_smem(nIa);
-  grid_acq_kernel<KID, NI_MAX, LATTICE><<<(unsigned)((size_t)T * p.chunks), GA_THREADS, smem, st>>>(p);
+  grid_acq_kernel<KID, NI_MAX, LATTICE, CH, MINB, NT><<<(unsigned)((size_t)T * p.chunks), GA_THREADS, smem, st>>>(p);
   return 0;
+}
+
+// tuning switch for experiments (B200BO_KB_TILES = 1|2 column tiles per MMA group); default = measured best
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+template <int KID, int NI_MAX, bool LATTICE>
+static int launch_grid_acq(const GridAcqParams& p, int T, cudaStream_t st) {
+  static const int tiles = env_int("B200BO_KB_TILES", 1);
+  if (!LATTICE) return launch_grid_acq_v<KID, NI_MAX, LATTICE, 2, (NI_MAX <= 8 ? 4 : 3), 1>(p, T, st);
+  if (tiles == 2) return launch_grid_acq_v<KID, NI_MAX, LATTICE, 2, (NI_MAX <= 8 ? 3 : 2), 2>(p, T, st);
+  return launch_grid_acq_v<KID, NI_MAX, LATTICE, 2, (NI_MAX <= 8 ? 4 : 3), 1>(p, T, st);
 }
 
 template <int KID, bool LATTICE>
@@ -398,8 +671,9 @@ static int grid_acq_common(bool lattice, const double* grid, int G, int Gx, int 
   p.Gx = Gx; p.Gy = Gy; p.x0 = x0; p.y0 = y0; p.h = h; p.ktab = ktab; p.ktab_id = ktab_id;
   int rc;
   if (lattice) {
-    // table look-ups do not depend on the kernel family: one instantiation serves all four
-    rc = dispatch_ni<B200BO_KERNEL_MATERN52, true>(p, T, st);
+    // table look-ups do not depend on the kernel family: one set of instantiations serves all four
+    static const int legacy = env_int("B200BO_KB_LEGACY", 0);
+    rc = legacy ? dispatch_ni<B200BO_KERNEL_MATERN52, true>(p, T, st) : dispatch_lattice(p, T, st);
   } else {
     switch (kernel_id) {
       case B200BO_KERNEL_RBF: rc = dispatch_ni<B200BO_KERNEL_RBF, false>(p, T, st); break;

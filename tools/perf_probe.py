@@ -29,7 +29,8 @@ def timeit(fn, reps=3):
 rows = []
 lat = ops.Lattice.from_points(grid)
 ktab = ops.kernel_table(theta[:1].contiguous(), 3, lat)
-for n in [10, 16, 24, 32, 40, 48, 64, 80, 96, 110, 128]:
+NS = [int(v) for v in os.environ.get('NS', '10,16,24,32,40,48,64,80,96,110,128').split(',')]
+for n in NS:
     n_max = n
     idx = np.stack([rng.choice(G, n, replace=False) for _ in range(T)])
     X = grid[torch.as_tensor(idx, device=dev)].contiguous()
@@ -49,6 +50,7 @@ for n in [10, 16, 24, 32, 40, 48, 64, 80, 96, 110, 128]:
     print(rows[-1], flush=True)
 json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "perf_probe.json"), "w"))
 # stepwise BO run
+if os.environ.get('NO_BO'): sys.exit(0)
 Tb = int(os.environ.get("TB", 1024)); iters = int(os.environ.get("ITERS", 50))
 idx = np.stack([rng.choice(G, 10, replace=False) for _ in range(Tb)])
 X0 = grid[torch.as_tensor(idx, device=dev)].contiguous()
