@@ -110,6 +110,19 @@ int b200bo_gp_assemble_chol(const double* X, const double* y, const int32_t* n, 
                             double* Linv, double* alpha, double* logdet, double* wfrag, int32_t* status, int T,
                             int n_max, int n_hint, int kernel_id, void* stream);
 
+/* K-A append variant: one observation was appended (it is row n[t]-1) and theta is unchanged —
+ * the fixed-hyper-parameter loops re-create the same model plus one point per iteration
+ * (Src/BO.py:416-429). Extends L^-1 (wfrag, in/out), z = L^-1 (y - c) (zvec (T,n_max), in/out) and
+ * recomputes alpha in O(n^2). wfrag rows beyond the old n must be zero (zero-initialise the buffer).
+ * n_redo (T) int32 out: 0, or n[t] for trials whose new pivot was not positive — pass it as `n` to
+ * b200bo_gp_assemble_chol (+ b200bo_gp_zvec) right after to refactorise those with the jitter rule.
+ * b200bo_gp_zvec: z = L^-1 (y - c) from a fresh factorisation. */
+int b200bo_gp_chol_append(const double* X, const double* y, const int32_t* n, const double* theta, double* wfrag,
+                          double* zvec, double* alpha, int32_t* n_redo, int32_t* status, int T, int n_max, int kernel_id,
+                          void* stream);
+int b200bo_gp_zvec(const double* y, const int32_t* n, const double* theta, const double* wfrag, double* zvec, int T,
+                   int n_max, void* stream);
+
 /* ---- K-B  fused grid posterior + acquisition + arg-max --------------------------
  * replaces ExpectedImprovement(model,best_f) + optimize_acqf over the box (BO.py:158-161,
  * 72-83) by a dense arg-max over the candidate grid (the north-star redesign).

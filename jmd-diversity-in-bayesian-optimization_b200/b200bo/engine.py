@@ -33,7 +33,7 @@ class BatchedBO:
 
     def __init__(self, grid, obj, surf_id, X0, y0, max_iter, theta=None, kernel_id=ops.MATERN52, acq_id=ops.EI,
                  acq_param=0.0, tol=0.1, optimal_y=100.0, var_floor=ops.VAR_FLOOR, fitter=None, check_every=8,
-                 lattice="auto"):
+                 lattice="auto", append=True):
         dev = grid.device
         if dev.type != "cuda":
             raise ops._lib.B200boError("BatchedBO needs CUDA tensors: the engine has no CPU path")
@@ -65,7 +65,11 @@ class BatchedBO:
         self.kernel_id, self.acq_id, self.acq_param = int(kernel_id), int(acq_id), float(acq_param)
         self.tol, self.optimal_y, self.var_floor = float(tol), float(optimal_y), float(var_floor)
         self.alpha = torch.zeros((T, n_max), dtype=f64, device=dev)
-        self.wfrag = torch.empty((T, ops.wfrag_doubles(n_max)), dtype=f64, device=dev)
+        self.wfrag = torch.zeros((T, ops.wfrag_doubles(n_max)), dtype=f64, device=dev)
+        # fixed theta: L^-1 grows by one row per iteration (rank-1 append) instead of being refactorised
+        self.append = bool(append) and self.fixed
+        self.zvec = torch.zeros((T, n_max), dtype=f64, device=dev) if self.append else None
+        self.n_redo = torch.zeros(T, dtype=i32, device=dev) if self.append else None
         self.best_f = torch.empty(T, dtype=f64, device=dev)
         self.yall = torch.zeros((T, self.max_iter + 2), dtype=f64, device=dev)
         self.picked = torch.empty((T, max(self.max_iter, 1)), dtype=i32, device=dev)
@@ -104,6 +108,8 @@ class BatchedBO:
         self.status.zero_()
         self.nit.zero_()
         self.alpha.zero_()
+        if self.append:
+            self.wfrag.zero_()
         self.launches = 0
 
     def _timed(self, name, n, fn):
@@ -121,12 +127,27 @@ class BatchedBO:
             self.fitter.fit_into(self.X, self.y, self.n, self.kernel_id, self.theta, self.status, n_hint)
             self.thetas[:, it] = self.theta
             self.launches += self.fitter.last_launches
-        self._timed("gp_chol", n_hint, lambda: ops.gp_assemble_chol_into(
-            self.X, self.y, self.n, self.theta, self.kernel_id, self.alpha, self.wfrag, self.status, n_hint=n_hint))
+        self._timed("gp_chol", n_hint, lambda: self._factorise(it, n_hint))
         self._timed("grid_acq", n_hint, lambda: self._acquire(n_hint))
         ops.bo_update(self.grid, self.obj, self.surf_id, self.arg_idx, self.X, self.y, self.n, self.best_f, self.yall,
                       self.picked, self.nit, self.max_iter, it, self.tol, self.optimal_y)
         self.launches += 4
+
+    def _factorise(self, it, n_hint):
+        if not self.append or it == 0:
+            ops.gp_assemble_chol_into(self.X, self.y, self.n, self.theta, self.kernel_id, self.alpha, self.wfrag,
+                                      self.status, n_hint=n_hint)
+            if self.append:
+                ops.gp_zvec(self.y, self.n, self.theta, self.wfrag, self.zvec)
+                self.launches += 1
+            return
+        ops.gp_chol_append(self.X, self.y, self.n, self.theta, self.kernel_id, self.wfrag, self.zvec, self.alpha,
+                           self.n_redo, self.status)
+        # trials whose new pivot was not positive (none in practice) are refactorised with the jitter rule
+        ops.gp_assemble_chol_into(self.X, self.y, self.n_redo, self.theta, self.kernel_id, self.alpha, self.wfrag,
+                                  self.status, n_hint=n_hint)
+        ops.gp_zvec(self.y, self.n_redo, self.theta, self.wfrag, self.zvec)
+        self.launches += 2
 
     def _acquire(self, n_hint):
         if self.lattice is not None:

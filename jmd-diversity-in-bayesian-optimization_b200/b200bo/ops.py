@@ -234,6 +234,20 @@ def gp_assemble_chol_into(X, y, n, theta, kernel_id, alpha, wfrag, status, n_hin
                                       _ptr(status), T, n_max, int(n_hint), int(kernel_id), _stream()), "gp_assemble_chol")
 
 
+def gp_chol_append(X, y, n, theta, kernel_id, wfrag, zvec, alpha, n_redo, status):
+    """K-A append variant (in place on wfrag / zvec / alpha); n_redo marks trials needing a full refactorisation."""
+    lib = _lib.load()
+    T, n_max = y.shape
+    check(lib.b200bo_gp_chol_append(_ptr(X), _ptr(y), _ptr(n), _ptr(theta), _ptr(wfrag), _ptr(zvec), _ptr(alpha),
+                                    _ptr(n_redo), _ptr(status), T, n_max, int(kernel_id), _stream()), "gp_chol_append")
+
+
+def gp_zvec(y, n, theta, wfrag, zvec):
+    lib = _lib.load()
+    T, n_max = y.shape
+    check(lib.b200bo_gp_zvec(_ptr(y), _ptr(n), _ptr(theta), _ptr(wfrag), _ptr(zvec), T, n_max, _stream()), "gp_zvec")
+
+
 def mll_value_grad(X, y, n, raw, kernel_id, status=None, n_hint=0, value=None, grad=None):
     """K-C. raw (T,4) f64 = (noise, c, raw_outputscale, raw_lengthscale) -> value (T,), grad (T,4), status."""
     lib = _lib.load()

@@ -23,17 +23,18 @@ def _setup(golden, lattice_grid, T, n0, seed):
     return obj, surf_id, X0, y0
 
 
+@pytest.mark.parametrize("append", [True, False])
 @pytest.mark.parametrize("lattice", ["auto", None])
 @pytest.mark.parametrize("kid,acq", [(3, 0), (0, 0), (3, 1)])
-def test_fixed_theta_loop_matches_oracle(golden, lattice_grid, kid, acq, lattice):
+def test_fixed_theta_loop_matches_oracle(golden, lattice_grid, kid, acq, lattice, append):
     from b200bo import engine
     T, n0, max_iter = 12, 10, 25
     obj, surf_id, X0, y0 = _setup(golden, lattice_grid, T, n0, seed=kid * 10 + acq)
     theta = ogp.raw_to_theta(AUTHOR_THETA_RAW)
     t = lambda a, dt=None: torch.as_tensor(a, device=DEV, dtype=dt)
     bo = engine.BatchedBO(t(lattice_grid), t(obj), t(surf_id), t(X0), t(y0), max_iter, theta=t(theta), kernel_id=kid,
-                          acq_id=acq, acq_param=4.0, tol=0.1, lattice=lattice)
-    assert (bo.lattice is not None) == (lattice == "auto")
+                          acq_id=acq, acq_param=4.0, tol=0.1, lattice=lattice, append=append)
+    assert (bo.lattice is not None) == (lattice == "auto") and bo.append == append
     res = bo.run()
     torch.cuda.synchronize()
     yall = res.yall.cpu().numpy(); picked = res.picked.cpu().numpy(); nit = res.nit.cpu().numpy()

@@ -234,3 +234,62 @@ def test_lattice_half_step_grid_and_off_lattice_flag(golden):
     st = ops.gp_assemble_chol(_to(X), _to(y), _to(n), _to(th), 3)
     b = ops.grid_posterior_acq_argmax_lattice(lat, ktab, None, _to(X), st["wfrag"], st["alpha"], _to(n), _to(th), _to(best), 3)
     assert b["status"][0].item() == 0 and (b["status"][1].item() & ops.ST_OFF_LATTICE)
+
+
+@pytest.mark.parametrize("kid", [0, 3])
+def test_rank1_append_matches_refactorisation(golden, lattice_grid, kid):
+    """K-A append variant: growing L^-1 / z / alpha one observation at a time equals a fresh factorisation."""
+    from b200bo import ops
+    n_max, T, n0 = 40, 6, 7
+    X, y, n_full, th = _make_batch(golden, lattice_grid, T, [n_max], n_max, seed=kid + 21, theta=_theta())
+    Xd, yd, thd = _to(X), _to(y), _to(th)
+    n = torch.full((T,), n0, dtype=torch.int32, device=DEV)
+    wf = torch.zeros((T, ops.wfrag_doubles(n_max)), dtype=torch.float64, device=DEV)
+    al = torch.zeros((T, n_max), dtype=torch.float64, device=DEV)
+    zv = torch.zeros((T, n_max), dtype=torch.float64, device=DEV)
+    st = torch.zeros(T, dtype=torch.int32, device=DEV)
+    redo = torch.zeros(T, dtype=torch.int32, device=DEV)
+    ops.gp_assemble_chol_into(Xd, yd, n, thd, kid, al, wf, st)
+    ops.gp_zvec(yd, n, thd, wf, zv)
+    for m in range(n0 + 1, n_max + 1):
+        n.fill_(m)
+        ops.gp_chol_append(Xd, yd, n, thd, kid, wf, zv, al, redo, st)
+        assert int(redo.max()) == 0 and int(st.max()) == 0
+        if m in (n0 + 1, 16, 17, 24, 33, n_max):
+            ref = ops.gp_assemble_chol(Xd, yd, n, thd, kid, want=("alpha", "wfrag", "Linv"))
+            nb = ((m + 7) // 8) * (((m + 7) // 8) + 1) * 32
+            a, b = wf[:, :nb].cpu().numpy(), ref["wfrag"][:, :nb].cpu().numpy()
+            assert np.allclose(a, b, rtol=1e-9, atol=1e-11 * np.abs(b).max()), (m, np.abs(a - b).max())
+            assert np.all(a[b == 0] == 0)
+            aa, ab = al[:, :m].cpu().numpy(), ref["alpha"][:, :m].cpu().numpy()
+            assert np.allclose(aa, ab, rtol=1e-8, atol=1e-10 * np.abs(ab).max()), (m, np.abs(aa - ab).max())
+            for t in range(T):
+                z_o = ref["Linv"][t, :m, :m].cpu().numpy() @ (y[t, :m] - th[t, 1])
+                assert np.allclose(zv[t, :m].cpu().numpy(), z_o, rtol=1e-8, atol=1e-10 * np.abs(z_o).max())
+
+
+def test_rank1_append_failure_is_handed_to_full_kernel():
+    """Appending a duplicate of an observation with zero noise makes the new pivot non-positive: n_redo flags the
+    trial and the full kernel repairs it with psd_safe_cholesky's jitter (status bit 0)."""
+    from b200bo import ops
+    n_max = 8
+    X = np.zeros((2, n_max, 2)); y = np.zeros((2, n_max))
+    X[:, :4] = [[1.0, 1.0], [5.0, 9.0], [20.0, 3.0], [1.0, 1.0]]
+    y[:, :4] = [1.0, 2.0, 3.0, 1.0]
+    th = np.array([[0.0, 0.0, 1.0, 5.0], [1e-2, 0.0, 1.0, 5.0]])
+    Xd, yd, thd = _to(X), _to(y), _to(th)
+    n = torch.full((2,), 3, dtype=torch.int32, device=DEV)
+    wf = torch.zeros((2, ops.wfrag_doubles(n_max)), dtype=torch.float64, device=DEV)
+    al = torch.zeros((2, n_max), dtype=torch.float64, device=DEV); zv = torch.zeros_like(al)
+    st = torch.zeros(2, dtype=torch.int32, device=DEV); redo = torch.zeros(2, dtype=torch.int32, device=DEV)
+    ops.gp_assemble_chol_into(Xd, yd, n, thd, 3, al, wf, st)
+    ops.gp_zvec(yd, n, thd, wf, zv)
+    n.fill_(4)
+    ops.gp_chol_append(Xd, yd, n, thd, 3, wf, zv, al, redo, st)
+    assert redo.tolist() == [4, 0] and st.tolist() == [0, 0]
+    ops.gp_assemble_chol_into(Xd, yd, redo, thd, 3, al, wf, st)
+    ops.gp_zvec(yd, redo, thd, wf, zv)
+    assert st.tolist() == [ogp.ST_JITTER, 0]
+    for t in range(2):
+        _, alpha, _, so = ogp.gp_state(X[t, :4], y[t, :4], th[t], 3)
+        assert np.allclose(al[t, :4].cpu().numpy(), alpha, rtol=1e-6, atol=1e-8 * np.abs(alpha).max())
