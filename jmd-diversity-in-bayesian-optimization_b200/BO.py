@@ -202,7 +202,7 @@ def _fixparam_to_theta(fixparam):
 
 
 def BOloop_batched(obj_tables, surf_id, init_X, init_y, max_iter, theta=None, grid=None, acq="EI", acq_param=0.0,
-                   tol=0.1, optimal_y=100.0, nu=2.5, covar="matern", device="cuda:0", lattice="auto"):
+                   tol=0.1, optimal_y=100.0, nu=2.5, covar="matern", device="cuda:0", lattice="auto", theta_rest=None):
     """Native batched entry: T trials in lock-step. obj_tables (S,G) f32 objective at every candidate, surf_id (T,),
     init_X (T,n0,2), init_y (T,n0); theta (4,) / (T,4) ACTUAL hyper-parameters or None (= fit before every
     acquisition). grid: (G,2) candidates or an ops.Lattice (default: the 100x100 lattice of data_gen.constructX).
@@ -219,12 +219,13 @@ def BOloop_batched(obj_tables, surf_id, init_X, init_y, max_iter, theta=None, gr
     bo = engine.BatchedBO(pts, t(obj_tables, torch.float32), t(surf_id, torch.int32), t(init_X, torch.float64),
                           t(init_y, torch.float64), max_iter, theta=None if theta is None else t(theta, torch.float64),
                           kernel_id=ops.kernel_id_from(nu, covar), acq_id=acq_id, acq_param=acq_param, tol=tol,
-                          optimal_y=optimal_y, fitter=fitter, lattice=lat)
+                          optimal_y=optimal_y, fitter=fitter, lattice=lat,
+                          theta_rest=None if theta_rest is None else t(theta_rest, torch.float64))
     return bo.run()
 
 
 def _single(obj_func, max_iter, X, Y, theta, bounds, tol, nu, covar, minstate, optimal_y, budget, device,
-            theta_first_only=None):
+            theta_rest=None):
     if nu > 2.5:
         covar = "rbf"                                        # BO.py:133-134
     nt = 10 if len(X) > 10 else len(X)
@@ -237,7 +238,7 @@ def _single(obj_func, max_iter, X, Y, theta, bounds, tol, nu, covar, minstate, o
     y0 = train_obj.double().reshape(1, nt)
     # error = optimal_y - yopt on the (possibly negated) objective, exactly as BO.py:241 computes it
     res = BOloop_batched(table, np.zeros(1, dtype=np.int32), X0, y0, max_iter, theta=theta, grid=lat, tol=tol,
-                         optimal_y=optimal_y, nu=nu, covar=covar, device=device)
+                         optimal_y=optimal_y, nu=nu, covar=covar, device=device, theta_rest=theta_rest)
     torch.cuda.synchronize(dev)
     r = _pack_result(res, 0, nt, max_iter, minstate, optimal_y, X)
     return r
@@ -254,9 +255,11 @@ def BOloop_fixparam(obj_func, max_iter, X, Y, fixparam, bounds=[(0, 100), (0, 10
                     reference_quirk=False):
     """BO with fixed hyper-parameters ``fixparam[name][0]`` (BO.py:380-461)."""
     theta = _fixparam_to_theta(fixparam)
-    if reference_quirk:
-        raise NotImplementedError("reference_quirk (defaults after the first iteration, BO.py:424-429) is not built yet")
-    return _single(obj_func, max_iter, X, Y, theta, bounds, tol, nu, covar, minstate, optimal_y, budget, device)
+    # as coded, only the first model carries fixparam; every re-created model keeps gpytorch's defaults
+    # (noise 2, constant 0, outputscale = lengthscale = softplus(0)), BO.py:392-395 vs :424-429
+    rest = np.array([2.0, 0.0, np.log(2.0), np.log(2.0)]) if reference_quirk else None
+    return _single(obj_func, max_iter, X, Y, theta, bounds, tol, nu, covar, minstate, optimal_y, budget, device,
+                   theta_rest=rest)
 
 
 def BOloop_singleopt(obj_func, max_iter, X, Y, bounds=[(0, 100), (0, 100)], verbose=False, tol=1, nu=2.5, covar="matern",

@@ -33,7 +33,7 @@ class BatchedBO:
 
     def __init__(self, grid, obj, surf_id, X0, y0, max_iter, theta=None, kernel_id=ops.MATERN52, acq_id=ops.EI,
                  acq_param=0.0, tol=0.1, optimal_y=100.0, var_floor=ops.VAR_FLOOR, fitter=None, check_every=8,
-                 lattice="auto", append=True):
+                 lattice="auto", append=True, theta_rest=None):
         dev = grid.device
         if dev.type != "cuda":
             raise ops._lib.B200boError("BatchedBO needs CUDA tensors: the engine has no CPU path")
@@ -62,6 +62,14 @@ class BatchedBO:
                 raise ValueError("theta=None needs a fitter")
             self.theta = torch.zeros((T, 4), dtype=f64, device=dev)
         self.fitter = fitter
+        # reference_quirk: BOloop_fixparam as coded copies fixparam into the first model only; every model
+        # re-created after an append keeps gpytorch's defaults (Src/BO.py:392-395 vs :424-429). theta_rest, when
+        # given, replaces theta from the second iteration on.
+        self.theta_rest = None
+        if theta_rest is not None:
+            tr = torch.as_tensor(theta_rest, dtype=f64, device=dev)
+            self.theta_rest = (tr.expand(T, 4) if tr.dim() == 1 else tr).contiguous().clone()
+            self.theta_first = self.theta.clone()
         self.kernel_id, self.acq_id, self.acq_param = int(kernel_id), int(acq_id), float(acq_param)
         self.tol, self.optimal_y, self.var_floor = float(tol), float(optimal_y), float(var_floor)
         self.alpha = torch.zeros((T, n_max), dtype=f64, device=dev)
@@ -110,6 +118,8 @@ class BatchedBO:
         self.alpha.zero_()
         if self.append:
             self.wfrag.zero_()
+        if self.theta_rest is not None:
+            self._switch_theta(self.theta_first)
         self.launches = 0
 
     def _timed(self, name, n, fn):
@@ -121,8 +131,17 @@ class BatchedBO:
         e1.record()
         self.profile.append((name, n, e0, e1))
 
+    def _switch_theta(self, th):
+        self.theta.copy_(th)
+        if self.lattice is not None and self.fixed:
+            uniq, inv = torch.unique(self.theta, dim=0, return_inverse=True)
+            self.ktab = ops.kernel_table(uniq.contiguous(), self.kernel_id, self.lattice)
+            self.ktab_id = inv.to(torch.int32).contiguous()
+
     def step(self, it: int):
         n_hint = self.n0 + it
+        if self.theta_rest is not None and it == 1:
+            self._switch_theta(self.theta_rest)
         if not self.fixed:
             self.fitter.fit_into(self.X, self.y, self.n, self.kernel_id, self.theta, self.status, n_hint)
             self.thetas[:, it] = self.theta
@@ -134,7 +153,7 @@ class BatchedBO:
         self.launches += 4
 
     def _factorise(self, it, n_hint):
-        if not self.append or it == 0:
+        if not self.append or it == 0 or (it == 1 and self.theta_rest is not None):
             ops.gp_assemble_chol_into(self.X, self.y, self.n, self.theta, self.kernel_id, self.alpha, self.wfrag,
                                       self.status, n_hint=n_hint)
             if self.append:

@@ -25,6 +25,7 @@
 namespace b200bo {
 
 constexpr int GA_THREADS = 128;
+static int env_int(const char* name, int dflt);
 constexpr int GA_WARPS = GA_THREADS / 32;
 
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
@@ -375,9 +376,10 @@ __device__ __forceinline__ void lattice_tile(const double* __restrict__ wsm, con
   }
 }
 
-template <int NI>
-__global__ void __launch_bounds__(GA_THREADS, (NI <= 8 ? 5 : 4))
+template <int NI, int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS == 128 ? (NI <= 8 ? 5 : 4) : (THREADS == 256 ? 2 : 1)))
 grid_acq_lattice_kernel(const GridAcqParams p) {
+  constexpr int NWARPS = THREADS / 32;
   extern __shared__ double sm[];
   const int t = blockIdx.x / p.chunks;
   const int chunk = blockIdx.x - t * p.chunks;
@@ -398,14 +400,14 @@ grid_acq_lattice_kernel(const GridAcqParams p) {
   double* wsm = sm;                       // NI (NI + 1) * 32
   double* al = sm + (size_t)NI * (NI + 1) * 32;
   int* xyi = reinterpret_cast<int*>(al + npad);
-  __shared__ double red_val[GA_WARPS];
-  __shared__ int red_idx[GA_WARPS];
+  __shared__ double red_val[NWARPS];
+  __shared__ int red_idx[NWARPS];
   __shared__ int red_flag;
   {
     const double2* src = reinterpret_cast<const double2*>(p.wfrag + (size_t)t * p.wstride);
     double2* dst = reinterpret_cast<double2*>(wsm);
-    for (int e = threadIdx.x; e < nblk * 16; e += GA_THREADS) dst[e] = src[e];
-    for (int j = threadIdx.x; j < npad; j += GA_THREADS) {
+    for (int e = threadIdx.x; e < nblk * 16; e += THREADS) dst[e] = src[e];
+    for (int j = threadIdx.x; j < npad; j += THREADS) {
       const bool v = j < n;
       const double x = v ? p.X[((size_t)t * p.n_max + j) * 2] : p.x0;
       const double y = v ? p.X[((size_t)t * p.n_max + j) * 2 + 1] : p.y0;
@@ -431,7 +433,7 @@ grid_acq_lattice_kernel(const GridAcqParams p) {
   int best_i = INT_MAX;
   int flags = 0;
 
-  for (int base = col0 + warp * 32; base < col_end; base += GA_WARPS * 32) {
+  for (int base = col0 + warp * 32; base < col_end; base += NWARPS * 32) {
     double my_ss = 0.0, my_mu = 0.0;
     int my_masked = 0;
 #pragma unroll 1
@@ -492,7 +494,7 @@ grid_acq_lattice_kernel(const GridAcqParams p) {
   if (threadIdx.x == 0) {
     double bv = red_val[0];
     int bi = red_idx[0];
-    for (int w = 1; w < GA_WARPS; ++w)
+    for (int w = 1; w < NWARPS; ++w)
       if (better(red_val[w], red_idx[w], bv, bi)) { bv = red_val[w]; bi = red_idx[w]; }
     p.part_val[(size_t)t * p.chunks + chunk] = bv;
     p.part_idx[(size_t)t * p.chunks + chunk] = bi;
@@ -500,13 +502,24 @@ grid_acq_lattice_kernel(const GridAcqParams p) {
   }
 }
 
+template <int NI, int THREADS>
+static int launch_lattice_t(const GridAcqParams& p, int T, cudaStream_t st) {
+  size_t smem = ((size_t)NI * (NI + 1) * 32 + 8 * (size_t)NI) * sizeof(double) + 8 * (size_t)NI * sizeof(int);
+  cudaError_t e = cudaFuncSetAttribute(grid_acq_lattice_kernel<NI, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_status(e, "grid_posterior_acq_argmax_lattice: smem attribute");
+  grid_acq_lattice_kernel<NI, THREADS><<<(unsigned)((size_t)T * p.chunks), THREADS, smem, st>>>(p);
+  return 0;
+}
+
 template <int NI>
 static int launch_lattice(const GridAcqParams& p, int T, cudaStream_t st) {
-  size_t smem = ((size_t)NI * (NI + 1) * 32 + 8 * (size_t)NI) * sizeof(double) + 8 * (size_t)NI * sizeof(int);
-  cudaError_t e = cudaFuncSetAttribute(grid_acq_lattice_kernel<NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return cuda_status(e, "grid_posterior_acq_argmax_lattice: smem attribute");
-  grid_acq_lattice_kernel<NI><<<(unsigned)((size_t)T * p.chunks), GA_THREADS, smem, st>>>(p);
-  return 0;
+  // CTA size: with >= 9 row blocks the L^-1 fragments of four 128-thread CTAs leave the SM's L1 too small for the
+  // kernel table (look-ups then pay L2 latency); two 256-thread CTAs keep the same 16 warps/SM and the table in L1.
+  // Measured (tools/perf_probe.py): n = 110: 0.80 -> 0.85 of FP64 peak; n <= 64: 128 threads are better.
+  static const int thr = env_int("B200BO_KB_THREADS", 0);
+  const int use = thr ? thr : (NI >= 9 ? 256 : 128);
+  if (use == 256) return launch_lattice_t<NI, 256>(p, T, st);
+  return launch_lattice_t<NI, 128>(p, T, st);
 }
 
 static int dispatch_lattice(const GridAcqParams& p, int T, cudaStream_t st) {

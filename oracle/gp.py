@@ -295,7 +295,7 @@ def raw_to_theta(raw):
 # ------------------------------------------------------------------ BO loop on a grid
 
 def bo_loop(grid, obj_values, X0, y0, max_iter, theta=None, kernel_id=MATERN52, acq_id=EI, acq_param=0.0,
-            tol=0.1, optimal_y=100.0, var_floor=VAR_FLOOR, fit=None, record=False):
+            tol=0.1, optimal_y=100.0, var_floor=VAR_FLOOR, fit=None, record=False, theta_rest=None):
     """BOloop / BOloop_fixparam semantics (BO.py:141-278, 380-461) with the
     continuous ``optimize_acqf`` replaced by a dense arg-max over ``grid``.
 
@@ -318,6 +318,8 @@ def bo_loop(grid, obj_values, X0, y0, max_iter, theta=None, kernel_id=MATERN52, 
     while error > tol and it < max_iter:
         it += 1
         th = theta if theta is not None else raw_to_theta(fit(X, y, kernel_id))
+        if theta_rest is not None and it > 1:
+            th = theta_rest          # BOloop_fixparam as coded: defaults after the first re-created model (BO.py:424-429)
         thetas.append(np.array(th, dtype=np.float64))
         idx, val, st = grid_step(grid, X, y, th, kernel_id, acq_id, acq_param, var_floor)
         status |= st

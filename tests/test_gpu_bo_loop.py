@@ -69,3 +69,24 @@ def test_tol_disabled_runs_all_iterations_and_never_repeats_a_point(golden, latt
     yall = res.yall.cpu().numpy()
     assert np.all(np.diff(yall, axis=1) >= 0)                          # best-so-far is monotone
     assert np.array_equal(yall[:, -1], yall[:, -2])                    # final append (BO.py:262)
+
+
+def test_reference_quirk_defaults_after_first_iteration(golden, lattice_grid):
+    """BOloop_fixparam as coded (BO.py:392-395 vs :424-429): fixparam only for the first acquisition, gpytorch
+    defaults (noise 2, c 0, s = l = log 2) afterwards -> near space-filling search."""
+    from b200bo import engine
+    T, n0, max_iter = 8, 10, 20
+    obj, surf_id, X0, y0 = _setup(golden, lattice_grid, T, n0, seed=5)
+    theta = ogp.raw_to_theta(AUTHOR_THETA_RAW)
+    rest = np.array([2.0, 0.0, np.log(2.0), np.log(2.0)])
+    t = lambda a: torch.as_tensor(a, device=DEV)
+    bo = engine.BatchedBO(t(lattice_grid), t(obj), t(surf_id), t(X0), t(y0), max_iter, theta=t(theta), tol=0.1, theta_rest=t(rest))
+    for rep in range(2):                                     # second pass exercises reset() with a theta switch
+        if rep:
+            bo.reset(t(X0), t(y0))
+        res = bo.run()
+        for i in range(T):
+            o = ogp.bo_loop(lattice_grid, obj[surf_id[i]], X0[i], y0[i], max_iter, theta=theta, tol=0.1, theta_rest=rest)
+            assert int(res.nit[i]) == o["nit"]
+            assert np.array_equal(res.picked[i, :o["nit"]].cpu().numpy(), o["idx"])
+            assert np.array_equal(res.yall[i].cpu().numpy(), o["yall"])
