@@ -50,6 +50,10 @@ def parse():
     ap.add_argument("--cpu-trials-per-core", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dpp", action="store_true")
+    ap.add_argument("--posterior", default="full", choices=["full", "incremental"],
+                    help="full: O(n^2) fused recomputation per iteration (headline, north-star kernel); incremental: "
+                         "O(n) rank-1 posterior update per candidate with (mu, var) state in HBM")
+    ap.add_argument("--no-incremental-extra", action="store_true")
     return ap.parse_args()
 
 
@@ -206,7 +210,7 @@ def run_b200(args):
     theta = torch.tensor(THETA, dtype=torch.float64, device=dev)
 
     bo = engine.BatchedBO(grid, obj_dev, sid_d, X0_d, y0_d, iters, theta=theta, kernel_id=ops.MATERN52, acq_id=ops.EI,
-                          tol=-1.0, lattice=lat, check_every=0)
+                          tol=-1.0, lattice=lat, check_every=0, posterior=args.posterior)
     yall_host = torch.empty((T, iters + 2), dtype=torch.float64).pin_memory()
     nit_host = torch.empty(T, dtype=torch.int32).pin_memory()
 
@@ -268,6 +272,7 @@ def run_b200(args):
     # ---- roofline of the dominant kernel (fused grid posterior + EI + arg-max), measured in the timed steps
     kb = [(n, e0.elapsed_time(e1)) for name, n, e0, e1 in prof if name == "grid_acq"]
     ka = [(n, e0.elapsed_time(e1)) for name, n, e0, e1 in prof if name == "gp_chol"]
+    ki = [(n, e0.elapsed_time(e1)) for name, n, e0, e1 in prof if name == "grid_inc"]
     flops = sum(T * G * (n * n + 17 * n + 30) for n, _ in kb)
     kb_ms = sum(ms for _, ms in kb)
     ka_ms = sum(ms for _, ms in ka)
@@ -290,6 +295,23 @@ def run_b200(args):
                 "gp_chol_share_of_step": ka_ms / ms_total if ms_total else None,
                 "launches_timed": len(kb)}
 
+    if args.posterior == "incremental":
+        # dominant kernel = grid_inc_kernel (+ the row append inside the same timed bracket): HBM-side model
+        # 32 B per candidate and launch (read + write of the two fp64 state words), first launch writes only
+        ki_ms = sum(ms for _, ms in ki)
+        hbm_bytes = sum(T * G * (16 if n == 1 else 32) for n, _ in ki)
+        hbm_peak = None
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+        except Exception:
+            pass
+        hbm_peak = hbm_peak or 6650.0
+        ach = hbm_bytes / (ki_ms * 1e-3) / 1e9 if ki_ms > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": "grid_inc_kernel (incremental K-B) + gp_append_kernel", "achieved": ach,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                    "bytes_model": "32 B per candidate-iteration (two fp64 state words read + written)",
+                    "note": "issue-bound above n ~ 20 (n table look-ups + n FMA per candidate), HBM-bound below",
+                    "kernel_share_of_step": ki_ms / ms_total if ms_total else None, "launches_timed": len(ki)}
     total_its = nit_sum * world            # every rank runs the same number of trial-iterations (tol disabled)
     per_step_ms = ms_total / args.steps
     value = total_its / (per_step_ms * 1e-3)
@@ -305,6 +327,27 @@ def run_b200(args):
             "gpu_launches": int(launches), "clocks": clocks, "status_bits_seen": status_max,
             "gathered_curves_shape": list(curves.shape)}
 
+    line["config"]["posterior"] = args.posterior
+    if rank == 0 and world == 1 and args.posterior == "full" and not args.no_incremental_extra:
+        # the same workload through the O(n) incremental posterior (not the headline: see DESIGN.md §3)
+        del bo
+        torch.cuda.empty_cache()
+        bo2 = engine.BatchedBO(grid, obj_dev, sid_d, X0_d, y0_d, iters, theta=theta, kernel_id=ops.MATERN52,
+                               acq_id=ops.EI, tol=-1.0, lattice=lat, check_every=0, posterior="incremental")
+
+        def step_inc():
+            bo2.reset(X0_d, y0_d)
+            return bo2.run()
+
+        for _ in range(max(1, args.warmup)):
+            r2 = step_inc()
+        ms_inc, r2 = timed(step_inc, args.steps)
+        agree = float((r2.picked == res.picked).all(dim=1).float().mean().item())
+        line["incremental"] = {"value": int(r2.nit.sum().item()) / (ms_inc / args.steps * 1e-3), "unit": "BO iterations/s",
+                               "ms_per_step": ms_inc / args.steps, "trials_with_identical_picks": agree,
+                               "note": "posterior='incremental': rank-1 update of (mu, var) per candidate, state in HBM; "
+                                       "same posterior as the headline path"}
+        del bo2
     if rank == 0 and world == 1 and not args.no_dpp:
         line["dpp"] = bench_dpp(dev)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

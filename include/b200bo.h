@@ -116,10 +116,11 @@ int b200bo_gp_assemble_chol(const double* X, const double* y, const int32_t* n, 
  * recomputes alpha in O(n^2). wfrag rows beyond the old n must be zero (zero-initialise the buffer).
  * n_redo (T) int32 out: 0, or n[t] for trials whose new pivot was not positive — pass it as `n` to
  * b200bo_gp_assemble_chol (+ b200bo_gp_zvec) right after to refactorise those with the jitter rule.
+ * wrow_out (T,n_max) optional: dense copy of the new row of L^-1 (input of the incremental K-B).
  * b200bo_gp_zvec: z = L^-1 (y - c) from a fresh factorisation. */
 int b200bo_gp_chol_append(const double* X, const double* y, const int32_t* n, const double* theta, double* wfrag,
-                          double* zvec, double* alpha, int32_t* n_redo, int32_t* status, int T, int n_max, int kernel_id,
-                          void* stream);
+                          double* zvec, double* alpha, double* wrow_out, int32_t* n_redo, int32_t* status, int T,
+                          int n_max, int kernel_id, void* stream);
 int b200bo_gp_zvec(const double* y, const int32_t* n, const double* theta, const double* wfrag, double* zvec, int T,
                    int n_max, void* stream);
 
@@ -157,6 +158,26 @@ int b200bo_grid_posterior_acq_argmax_lattice(int Gx, int Gy, double x0, double y
                                              double* arg_val, double* mu, double* var, double* acq, int32_t* status,
                                              int T, int n_max, int n_hint, int kernel_id, void* ws, size_t ws_bytes,
                                              void* stream);
+
+/* Incremental variant of K-B for fixed hyper-parameters on a lattice: the appended observation adds one
+ * row w of L^-1 (b200bo_gp_chol_append, wrow_out), so per candidate  v = sum_j w_j k(x_j, x),
+ * mu_state += v * z_n,  ss_state += v^2  (mu = c + mu_state, var = s - ss_state) — one length-n dot product
+ * instead of the O(n^2) product; the two state words per (trial, candidate) live in HBM (T,G) f64 each.
+ * ktab2 (H, 2Gy-1, 2Gx-1) from b200bo_kernel_table_signed; obs_mask (T, ceil(G/32)) uint32 observed-candidate
+ * bits (zero-initialise; the kernel sets the bit of observation n-1). first != 0: state starts from zero.
+ * acquire == 0: state update only (used while the initial set is fed row by row).
+ * Same posterior as the full kernels (rows summed in order); replaces the same reference lines. */
+int b200bo_kernel_table_signed(const double* theta, int H, int kernel_id, double h, int Gx, int Gy, double* ktab2,
+                               void* stream);
+size_t b200bo_grid_inc_workspace_bytes(int T, int G);
+int b200bo_grid_posterior_update_acq_argmax(int Gx, int Gy, double x0, double y0, double h, const double* ktab2,
+                                            const int32_t* ktab_id, const double* X, const double* wrow,
+                                            const double* zvec, const int32_t* n, const double* theta,
+                                            const double* best_f, double* mu_state, double* ss_state,
+                                            uint32_t* obs_mask, const uint8_t* extra_mask, int first, int acquire,
+                                            int acq_id, double acq_param, double var_floor, int32_t* arg_idx,
+                                            double* arg_val, double* acq, int32_t* status, int T, int n_max, void* ws,
+                                            size_t ws_bytes, void* stream);
 
 /* ---- K-C  marginal log-likelihood value and gradient ----------------------------
  * replaces ExactMarginalLogLikelihood + autograd inside fit_gpytorch_model (BO.py:144,189).

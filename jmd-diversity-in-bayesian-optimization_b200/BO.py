@@ -202,10 +202,11 @@ def _fixparam_to_theta(fixparam):
 
 
 def BOloop_batched(obj_tables, surf_id, init_X, init_y, max_iter, theta=None, grid=None, acq="EI", acq_param=0.0,
-                   tol=0.1, optimal_y=100.0, nu=2.5, covar="matern", device="cuda:0", lattice="auto", theta_rest=None):
+                   tol=0.1, optimal_y=100.0, nu=2.5, covar="matern", device="cuda:0", lattice="auto", theta_rest=None,
+                   posterior="full"):
     """Native batched entry: T trials in lock-step. obj_tables (S,G) f32 objective at every candidate, surf_id (T,),
     init_X (T,n0,2), init_y (T,n0); theta (4,) / (T,4) ACTUAL hyper-parameters or None (= fit before every
-    acquisition). grid: (G,2) candidates or an ops.Lattice (default: the 100x100 lattice of data_gen.constructX).
+    acquisition). posterior="incremental" (fixed theta, lattice candidates): O(n) posterior update per candidate. grid: (G,2) candidates or an ops.Lattice (default: the 100x100 lattice of data_gen.constructX).
     Returns b200bo.engine.BOResult (device tensors)."""
     dev = torch.device(device)
     t = lambda a, dt: torch.as_tensor(a, dtype=dt).to(dev).contiguous()
@@ -220,7 +221,7 @@ def BOloop_batched(obj_tables, surf_id, init_X, init_y, max_iter, theta=None, gr
                           t(init_y, torch.float64), max_iter, theta=None if theta is None else t(theta, torch.float64),
                           kernel_id=ops.kernel_id_from(nu, covar), acq_id=acq_id, acq_param=acq_param, tol=tol,
                           optimal_y=optimal_y, fitter=fitter, lattice=lat,
-                          theta_rest=None if theta_rest is None else t(theta_rest, torch.float64))
+                          theta_rest=None if theta_rest is None else t(theta_rest, torch.float64), posterior=posterior)
     return bo.run()
 
 

@@ -29,7 +29,7 @@ PROTOTYPES = {
     "b200bo_simplex_noise": (c_int, [c_uint64, P, P, P, c_longlong, P]),
     "b200bo_wfrag_doubles": (c_size_t, [c_int]),
     "b200bo_gp_assemble_chol": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
-    "b200bo_gp_chol_append": (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
+    "b200bo_gp_chol_append": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
     "b200bo_gp_zvec": (c_int, [P, P, P, P, P, c_int, c_int, P]),
     "b200bo_grid_acq_workspace_bytes": (c_size_t, [c_int, c_int]),
     "b200bo_grid_posterior_acq_argmax": (c_int, [P, c_int, P, P, P, P, P, P, P, c_int, c_int, c_double, c_double,
@@ -38,6 +38,11 @@ PROTOTYPES = {
     "b200bo_grid_posterior_acq_argmax_lattice": (c_int, [c_int, c_int, c_double, c_double, c_double, P, P, P, P, P, P, P, P,
                                                          P, c_int, c_int, c_double, c_double, P, P, P, P, P, P, c_int,
                                                          c_int, c_int, c_int, P, c_size_t, P]),
+    "b200bo_kernel_table_signed": (c_int, [P, c_int, c_int, c_double, c_int, c_int, P, P]),
+    "b200bo_grid_inc_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "b200bo_grid_posterior_update_acq_argmax": (c_int, [c_int, c_int, c_double, c_double, c_double, P, P, P, P, P, P, P, P, P,
+                                                        P, P, P, c_int, c_int, c_int, c_double, c_double, P, P, P, P,
+                                                        c_int, c_int, P, c_size_t, P]),
     "b200bo_mll_value_grad": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "b200bo_lbfgs_state_bytes": (c_size_t, [c_int]),
     "b200bo_lbfgs_init": (c_int, [P, P, P, c_int, P, P, c_int, c_double, P]),

@@ -33,7 +33,7 @@ class BatchedBO:
 
     def __init__(self, grid, obj, surf_id, X0, y0, max_iter, theta=None, kernel_id=ops.MATERN52, acq_id=ops.EI,
                  acq_param=0.0, tol=0.1, optimal_y=100.0, var_floor=ops.VAR_FLOOR, fitter=None, check_every=8,
-                 lattice="auto", append=True, theta_rest=None):
+                 lattice="auto", append=True, theta_rest=None, posterior="full"):
         dev = grid.device
         if dev.type != "cuda":
             raise ops._lib.B200boError("BatchedBO needs CUDA tensors: the engine has no CPU path")
@@ -87,6 +87,7 @@ class BatchedBO:
         self.arg_val = torch.empty(T, dtype=f64, device=dev)
         self.ws = ops.grid_acq_workspace(T, self.G, dev)
         self.check_every = int(check_every)
+        self.posterior = posterior
         # candidates on a regular lattice (data_gen.constructX) -> kernel values come from a table
         self.lattice = ops.Lattice.from_points(self.grid) if isinstance(lattice, str) and lattice == "auto" else lattice
         self.ktab = self.ktab_id = None
@@ -100,6 +101,21 @@ class BatchedBO:
                 self.ktab_id = torch.arange(T, dtype=i32, device=dev)
             else:
                 self.lattice = None
+        # incremental posterior (fixed theta on a lattice): per-candidate (mu - c, s - var) persist in HBM and every
+        # iteration folds in the one new row of L^-1 (csrc/grid_inc.cu) instead of recomputing the O(n^2) product
+        self.incremental = posterior == "incremental"
+        if self.incremental:
+            if not (self.fixed and self.lattice is not None and self.append and self.theta_rest is None):
+                raise ops._lib.B200boError("posterior='incremental' needs fixed theta, lattice candidates and append=True")
+            G = self.G
+            self.mu_s = torch.empty((T, G), dtype=f64, device=dev)
+            self.ss_s = torch.empty((T, G), dtype=f64, device=dev)
+            self.obs_mask = torch.zeros((T, (G + 31) // 32), dtype=i32, device=dev)
+            self.wrow = torch.zeros((T, n_max), dtype=f64, device=dev)
+            self.n_ramp = torch.zeros(T, dtype=i32, device=dev)
+            uniq, _ = torch.unique(self.theta, dim=0, return_inverse=True)
+            self.ktab2 = ops.kernel_table_signed(uniq.contiguous(), self.kernel_id, self.lattice)
+            self.ws_inc = ops.grid_inc_workspace(T, G, dev)
         self.thetas = None if self.fixed else torch.zeros((T, max(self.max_iter, 1), 4), dtype=f64, device=dev)
         self.launches = 0
         self.profile = None        # set to a list to collect (name, n, start_event, end_event) per launch
@@ -120,6 +136,9 @@ class BatchedBO:
             self.wfrag.zero_()
         if self.theta_rest is not None:
             self._switch_theta(self.theta_first)
+        if self.incremental:
+            self.obs_mask.zero_()
+            self.zvec.zero_()
         self.launches = 0
 
     def _timed(self, name, n, fn):
@@ -183,11 +202,35 @@ class BatchedBO:
                                           status=self.status, ws=self.ws, arg_idx=self.arg_idx, arg_val=self.arg_val,
                                           n_hint=n_hint)
 
+    def _inc_update(self, n_arr, first, acquire):
+        ops.gp_chol_append(self.X, self.y, n_arr, self.theta, self.kernel_id, self.wfrag, self.zvec, self.alpha, None,
+                           self.status, wrow_out=self.wrow)
+        ops.grid_posterior_update_acq_argmax(self.lattice, self.ktab2, self.ktab_id, self.X, self.wrow, self.zvec, n_arr,
+                                             self.theta, self.best_f, self.mu_s, self.ss_s, self.obs_mask, first, acquire,
+                                             self.acq_id, self.acq_param, self.var_floor, arg_idx=self.arg_idx,
+                                             arg_val=self.arg_val, status=self.status, ws=self.ws_inc)
+        self.launches += 3 if acquire else 2
+
+    def _step_incremental(self, it: int):
+        if it == 0:
+            # feed the initial set one observation at a time; the last one also acquires
+            for i in range(1, self.n0 + 1):
+                self.n_ramp.fill_(i)
+                self._timed("grid_inc", i, lambda: self._inc_update(self.n_ramp, i == 1, i == self.n0))
+        else:
+            self._timed("grid_inc", self.n0 + it, lambda: self._inc_update(self.n, False, True))
+        ops.bo_update(self.grid, self.obj, self.surf_id, self.arg_idx, self.X, self.y, self.n, self.best_f, self.yall,
+                      self.picked, self.nit, self.max_iter, it, self.tol, self.optimal_y)
+        self.launches += 1
+
     def run(self) -> BOResult:
         ops.bo_init(self.y, self.n, self.best_f, self.yall, self.picked, self.nit, self.max_iter, self.tol, self.optimal_y)
         self.launches += 1
         for it in range(self.max_iter):
-            self.step(it)
+            if self.incremental:
+                self._step_incremental(it)
+            else:
+                self.step(it)
             if self.check_every and (it + 1) % self.check_every == 0 and it + 1 < self.max_iter:
                 if not bool((self.n > 0).any()):        # every trial reached tol: stop enqueueing
                     break

@@ -234,12 +234,44 @@ def gp_assemble_chol_into(X, y, n, theta, kernel_id, alpha, wfrag, status, n_hin
                                       _ptr(status), T, n_max, int(n_hint), int(kernel_id), _stream()), "gp_assemble_chol")
 
 
-def gp_chol_append(X, y, n, theta, kernel_id, wfrag, zvec, alpha, n_redo, status):
-    """K-A append variant (in place on wfrag / zvec / alpha); n_redo marks trials needing a full refactorisation."""
+def gp_chol_append(X, y, n, theta, kernel_id, wfrag, zvec, alpha, n_redo, status, wrow_out=None):
+    """K-A append variant (in place on wfrag / zvec / alpha); n_redo marks trials needing a full refactorisation;
+    wrow_out (T,n_max) optionally receives the dense new row of L^-1."""
     lib = _lib.load()
     T, n_max = y.shape
     check(lib.b200bo_gp_chol_append(_ptr(X), _ptr(y), _ptr(n), _ptr(theta), _ptr(wfrag), _ptr(zvec), _ptr(alpha),
-                                    _ptr(n_redo), _ptr(status), T, n_max, int(kernel_id), _stream()), "gp_chol_append")
+                                    _ptr(wrow_out), _ptr(n_redo), _ptr(status), T, n_max, int(kernel_id), _stream()),
+          "gp_chol_append")
+
+
+def kernel_table_signed(theta, kernel_id, lat, out=None):
+    """(H, 2Gy-1, 2Gx-1) f64 signed-offset kernel table (input of the incremental K-B)."""
+    lib = _lib.load()
+    _cu(theta, torch.float64, "theta")
+    H = theta.shape[0]
+    if out is None:
+        out = torch.empty((H, 2 * lat.Gy - 1, 2 * lat.Gx - 1), dtype=torch.float64, device=theta.device)
+    check(lib.b200bo_kernel_table_signed(_ptr(theta), H, int(kernel_id), lat.h, lat.Gx, lat.Gy, _ptr(out), _stream()),
+          "kernel_table_signed")
+    return out
+
+
+def grid_inc_workspace(T: int, G: int, device) -> torch.Tensor:
+    nbytes = int(_lib.load().b200bo_grid_inc_workspace_bytes(int(T), int(G)))
+    return torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
+
+
+def grid_posterior_update_acq_argmax(lat, ktab2, ktab_id, X, wrow, zvec, n, theta, best_f, mu_state, ss_state, obs_mask,
+                                     first, acquire, acq_id=EI, acq_param=0.0, var_floor=VAR_FLOOR, extra_mask=None,
+                                     arg_idx=None, arg_val=None, acq_out=None, status=None, ws=None):
+    """Incremental K-B: fold the new row of L^-1 into (mu_state, ss_state) and, if ``acquire``, arg-max the acquisition."""
+    lib = _lib.load()
+    T, n_max = zvec.shape
+    check(lib.b200bo_grid_posterior_update_acq_argmax(
+        lat.Gx, lat.Gy, lat.x0, lat.y0, lat.h, _ptr(ktab2), _ptr(ktab_id), _ptr(X), _ptr(wrow), _ptr(zvec), _ptr(n),
+        _ptr(theta), _ptr(best_f), _ptr(mu_state), _ptr(ss_state), _ptr(obs_mask), _ptr(extra_mask), 1 if first else 0,
+        1 if acquire else 0, int(acq_id), float(acq_param), float(var_floor), _ptr(arg_idx), _ptr(arg_val), _ptr(acq_out),
+        _ptr(status), T, n_max, _ptr(ws), 0 if ws is None else ws.numel(), _stream()), "grid_posterior_update_acq_argmax")
 
 
 def gp_zvec(y, n, theta, wfrag, zvec):

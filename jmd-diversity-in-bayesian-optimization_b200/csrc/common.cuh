@@ -11,6 +11,10 @@ void set_error(const char* fmt, ...);
 int arg_error(const char* fmt, ...);     // records message, returns -1
 int cuda_status(cudaError_t e, const char* where);   // 0 or positive cudaError_t (records message)
 
+// per-trial reduction of the per-CTA (value, index) partials of the arg-max kernels (grid_acq.cu)
+void launch_argmax_finish(const double* part_val, const int32_t* part_idx, int chunks, int T, const int32_t* n,
+                          int32_t* arg_idx, double* arg_val, int32_t* status, cudaStream_t st);
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 #define B200BO_CHECK_LAUNCH(where) \

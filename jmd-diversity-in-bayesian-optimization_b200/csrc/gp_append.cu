@@ -58,8 +58,8 @@ __device__ __forceinline__ void tri_matvec_t(const double* __restrict__ wf, int 
 __global__ void __launch_bounds__(AP_WARPS * 32)
 gp_append_kernel(const double* __restrict__ X, const double* __restrict__ y, const int32_t* __restrict__ n_arr,
                  const double* __restrict__ theta, double* __restrict__ wfrag, double* __restrict__ zvec,
-                 double* __restrict__ alpha, int32_t* __restrict__ n_redo, int32_t* __restrict__ status, int T, int n_max,
-                 int kernel_id, size_t wstride) {
+                 double* __restrict__ alpha, double* __restrict__ wrow_out, int32_t* __restrict__ n_redo,
+                 int32_t* __restrict__ status, int T, int n_max, int kernel_id, size_t wstride) {
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * AP_WARPS + warp;
@@ -95,6 +95,8 @@ gp_append_kernel(const double* __restrict__ X, const double* __restrict__ y, con
       if (n_redo) n_redo[t] = n;
       else if (status) atomicOr(&status[t], B200BO_ST_CHOL_FAIL);
     }
+    if (wrow_out)                                 // no usable new row: the incremental posterior stays as it was
+      for (int c = lane; c <= m; c += 32) wrow_out[(size_t)t * n_max + c] = 0.0;
     return;
   }
   const double lam = sqrt(lam2), inv_lam = 1.0 / lam;
@@ -113,6 +115,7 @@ gp_append_kernel(const double* __restrict__ X, const double* __restrict__ y, con
       w = inv_lam;
     }
     wf[(size_t)(I * (I + 1) + (c >> 2)) * 32 + rl + (c & 3)] = w;
+    if (wrow_out) wrow_out[(size_t)t * n_max + c] = w;     // dense copy of the new row for the incremental posterior
   }
   zacc = warp_sum(zacc);
   const double znew = zacc + (y[(size_t)t * n_max + m] - cst) * inv_lam;
@@ -155,8 +158,8 @@ gp_zvec_kernel(const double* __restrict__ y, const int32_t* __restrict__ n_arr, 
 extern "C" {
 
 int b200bo_gp_chol_append(const double* X, const double* y, const int32_t* n, const double* theta, double* wfrag,
-                          double* zvec, double* alpha, int32_t* n_redo, int32_t* status, int T, int n_max, int kernel_id,
-                          void* stream) {
+                          double* zvec, double* alpha, double* wrow_out, int32_t* n_redo, int32_t* status, int T,
+                          int n_max, int kernel_id, void* stream) {
   using namespace b200bo;
   if (T < 0 || n_max < 1 || n_max > B200BO_NMAX) return arg_error("gp_chol_append: T=%d n_max=%d", T, n_max);
   if (kernel_id < 0 || kernel_id > 3) return arg_error("gp_chol_append: kernel_id=%d", kernel_id);
@@ -164,7 +167,7 @@ int b200bo_gp_chol_append(const double* X, const double* y, const int32_t* n, co
   if (!X || !y || !n || !theta || !wfrag || !zvec || !alpha) return arg_error("gp_chol_append: null pointer");
   size_t smem = (size_t)AP_WARPS * 3 * n_max * sizeof(double);
   gp_append_kernel<<<(T + AP_WARPS - 1) / AP_WARPS, AP_WARPS * 32, smem, as_stream(stream)>>>(
-      X, y, n, theta, wfrag, zvec, alpha, n_redo, status, T, n_max, kernel_id, b200bo_wfrag_doubles(n_max));
+      X, y, n, theta, wfrag, zvec, alpha, wrow_out, n_redo, status, T, n_max, kernel_id, b200bo_wfrag_doubles(n_max));
   B200BO_CHECK_LAUNCH("gp_chol_append");
   return 0;
 }

@@ -115,6 +115,7 @@ struct GridAcqParams {
   int n_cap;                // upper bound of n[t] over the launch (template / smem selection)
   size_t wstride;
   int chunks;
+  int prune;                // EI pruning allowed (exact; see grid_acq_lattice_kernel)
   int cols_per_cta;         // multiple of 32
   // lattice variant: candidates g <-> (g % Gx, g / Gx), x = x0 + h * ix; kernel values come from
   // ktab[slot][|dy| * Gx + |dx|] (built by kernel_table_kernel with the same device function)
@@ -432,6 +433,8 @@ grid_acq_lattice_kernel(const GridAcqParams p) {
   double best_v = -INFINITY;
   int best_i = INT_MAX;
   int flags = 0;
+  const bool prune = p.acq_id == B200BO_ACQ_EI && p.acq_out == nullptr && p.prune;
+  double wbest = 0.0, lthr = INFINITY;
 
   for (int base = col0 + warp * 32; base < col_end; base += NWARPS * 32) {
     double my_ss = 0.0, my_mu = 0.0;
@@ -466,20 +469,35 @@ grid_acq_lattice_kernel(const GridAcqParams p) {
       }
     }
     const int g = base + lane;
+    // EI pruning (exact): for mu < best_f, EI = sigma phi(u) + (mu - best_f) Phi(u) <= 0.39894 sqrt(s) exp(-u^2/2)
+    // because the posterior sigma never exceeds the prior sqrt(s). A candidate whose bound is below the warp's
+    // running maximum can neither win nor tie, so its sqrt / exp / erfc (~160 FP64-pipe slots) are skipped;
+    // the test itself is two multiplies. Off when the caller asked for the acquisition field.
+    if (prune) {
+      const double nb = warp_max(best_v);
+      if (nb > wbest) {                                   // uniform
+        wbest = nb;
+        lthr = log(kInvSqrt2Pi * sqrt(sc) / nb) * (1.0 + 1e-12) + 1e-12;
+      }
+    }
     if (g < col_end) {
       const double mu = cst + my_mu;
       const double var = sc - my_ss;
-      double a;
-      if (p.acq_id == B200BO_ACQ_UCB) a = acquisition<B200BO_ACQ_UCB>(mu, var, best_f, p.acq_param, p.var_floor);
-      else if (p.acq_id == B200BO_ACQ_PI) a = acquisition<B200BO_ACQ_PI>(mu, var, best_f, p.acq_param, p.var_floor);
-      else a = acquisition<B200BO_ACQ_EI>(mu, var, best_f, p.acq_param, p.var_floor);
+      const bool m = (p.mask_observed && my_masked) || (p.extra_mask && p.extra_mask[g]);
       if (p.mu_out) p.mu_out[(size_t)t * p.G + g] = mu;
       if (p.var_out) p.var_out[(size_t)t * p.G + g] = var;
-      if (p.acq_out) p.acq_out[(size_t)t * p.G + g] = a;
-      const bool m = (p.mask_observed && my_masked) || (p.extra_mask && p.extra_mask[g]);
-      if (!m) {
-        if (isnan(a) || a == INFINITY) flags |= B200BO_ST_NONFINITE;
-        if (!isnan(a) && better(a, g, best_v, best_i)) { best_v = a; best_i = g; }
+      const double d = mu - best_f;
+      const bool skip = prune && wbest > 0.0 && d < 0.0 && 0.5 * d * d > fmax(var, p.var_floor) * lthr;
+      if (!skip) {
+        double a;
+        if (p.acq_id == B200BO_ACQ_UCB) a = acquisition<B200BO_ACQ_UCB>(mu, var, best_f, p.acq_param, p.var_floor);
+        else if (p.acq_id == B200BO_ACQ_PI) a = acquisition<B200BO_ACQ_PI>(mu, var, best_f, p.acq_param, p.var_floor);
+        else a = acquisition<B200BO_ACQ_EI>(mu, var, best_f, p.acq_param, p.var_floor);
+        if (p.acq_out) p.acq_out[(size_t)t * p.G + g] = a;
+        if (!m) {
+          if (isnan(a) || a == INFINITY) flags |= B200BO_ST_NONFINITE;
+          if (!isnan(a) && better(a, g, best_v, best_i)) { best_v = a; best_i = g; }
+        }
       }
     }
   }
@@ -567,6 +585,11 @@ argmax_finish_kernel(const double* __restrict__ part_val, const int32_t* __restr
   }
   arg_idx[t] = bi;
   if (arg_val) arg_val[t] = bv;
+}
+
+void launch_argmax_finish(const double* part_val, const int32_t* part_idx, int chunks, int T, const int32_t* n,
+                          int32_t* arg_idx, double* arg_val, int32_t* status, cudaStream_t st) {
+  argmax_finish_kernel<<<(T + 127) / 128, 128, 0, st>>>(part_val, part_idx, chunks, T, n, arg_idx, arg_val, status);
 }
 
 inline int pick_chunks(int T, int G) {
@@ -673,6 +696,7 @@ static int grid_acq_common(bool lattice, const double* grid, int G, int Gx, int 
   p.acq_param = acq_id == B200BO_ACQ_UCB ? sqrt(acq_param) : acq_param;
   p.var_floor = var_floor;
   p.chunks = pick_chunks(T, G);
+  p.prune = env_int("B200BO_KB_PRUNE", 1);
   p.cols_per_cta = (((G + p.chunks - 1) / p.chunks + GA_THREADS - 1) / GA_THREADS) * GA_THREADS;
   p.part_val = reinterpret_cast<double*>(ws);
   p.part_idx = reinterpret_cast<int32_t*>(p.part_val + (size_t)T * p.chunks);
