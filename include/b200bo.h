@@ -201,6 +201,15 @@ int b200bo_lbfgs_step(void* state, double* xt, const double* value, const double
                       const int32_t* n_obs, double* theta_out, double* raw_out, double* mll_out, int32_t* iters_out,
                       int T, double lb_noise, double gtol, double ftol, int max_iter, int max_ls, void* stream);
 
+/* Fused fit: the whole L-BFGS run of every trial in ONE launch (one CTA per trial keeps the observations in
+ * shared memory and alternates marginal-likelihood evaluation and optimiser step until convergence) — same
+ * arithmetic and optimiser as the b200bo_mll_value_grad + b200bo_lbfgs_step rounds, without the per-round
+ * launches and without waiting for the slowest trial. max_rounds bounds the evaluations per trial. */
+int b200bo_gp_fit(const double* X, const double* y, const int32_t* n, const double* raw0, int raw0_per_trial,
+                  double* theta_out, double* raw_out, double* mll_out, int32_t* iters_out, int32_t* status, int T,
+                  int n_max, int n_hint, int kernel_id, double lb_noise, double gtol, double ftol, int max_iter,
+                  int max_ls, int max_rounds, void* stream);
+
 /* ---- batched BO loop bookkeeping (one thread per trial) ---------------------------
  * replaces the Python statements between two acquisitions in BOloop / BOloop_fixparam:
  * objective look-up (Src/BO.py:104), append (:164-165), yopt / yall.append (:168-169),

@@ -17,7 +17,7 @@ NOISE_LB = 1e-4                      # botorch default GaussianLikelihood: Great
 
 class LBFGSFitter:
     def __init__(self, T: int, device, raw0=DEFAULT_RAW, gtol=1e-5, ftol=2.220446049250313e-9, max_iter=200,
-                 max_ls=30, max_rounds=600, poll=8):
+                 max_ls=30, max_rounds=600, poll=8, fused=True):
         lib = _lib.load()
         self.T = int(T)
         dev = torch.device(device)
@@ -37,12 +37,22 @@ class LBFGSFitter:
         self.max_rounds, self.poll = int(max_rounds), int(poll)
         self.last_launches = 0
         self.last_rounds = 0
+        self.fused = bool(fused)
 
     def fit_into(self, X, y, n, kernel_id, theta_out, status=None, n_hint=0):
         """Fit every trial with n[t] > 0 from the default start; writes ACTUAL theta (T,4) into theta_out."""
         lib = _lib.load()
         p, s = ops._ptr, ops._stream()
         T = self.T
+        if self.fused:
+            # one launch: every trial runs its own L-BFGS to convergence inside its CTA (csrc/gp_chol.cu:gp_fit_kernel)
+            check(lib.b200bo_gp_fit(p(X), p(y), p(n), p(self.raw0), self.raw0_per_trial, p(theta_out), p(self.raw),
+                                    p(self.mll), p(self.iters), p(status if status is not None else self.kc_status), T,
+                                    y.shape[1], int(n_hint), int(kernel_id), NOISE_LB, self.gtol, self.ftol, self.max_iter,
+                                    self.max_ls, self.max_rounds, s), "gp_fit")
+            self.last_launches = 1
+            self.last_rounds = 0
+            return theta_out
         check(lib.b200bo_lbfgs_init(p(self.state), p(self.xt), p(self.raw0), self.raw0_per_trial, p(self.n_eval), p(n), T,
                                     NOISE_LB, s), "lbfgs_init")
         launches = 1

@@ -241,3 +241,34 @@ def test_single_call_entry_points(golden):
     idx, _, _ = ogp.grid_step(grid, tx.numpy().astype(np.float64), ty.numpy().reshape(-1).astype(np.float64), model.theta(), 3)
     assert np.array_equal(new_x.numpy()[0].astype(np.float64), grid[idx])
     assert new_obj.item() == f(grid[idx][None])[0].astype(np.float32)
+
+
+def test_fused_fit_kernel_equals_round_based_fit(golden, lattice_grid):
+    """gp_fit_kernel (one launch, one CTA per trial) runs the same optimiser on the same arithmetic as the
+    mll_value_grad + lbfgs_step rounds: identical optimum, iteration and evaluation counts."""
+    from b200bo import fit
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(5)
+    surf = golden("wildcat.npz")["surf_1"]
+    T, n_max = 40, 64
+    X = np.zeros((T, n_max, 2)); y = np.zeros((T, n_max)); n = np.zeros(T, dtype=np.int32)
+    for t in range(T):
+        n[t] = [10, 12, 25, 40, 64][t % 5]
+        idx = rng.choice(10000, n[t], replace=False)
+        X[t, :n[t]] = lattice_grid[idx]
+        y[t, :n[t]] = surf[:100, :100].reshape(-1)[idx]
+    n[3] = 0
+    to = lambda a: torch.as_tensor(a, device=dev)
+    outs = []
+    for fused in (True, False):
+        f = fit.LBFGSFitter(T, dev, fused=fused)
+        theta = torch.zeros((T, 4), dtype=torch.float64, device=dev)
+        f.fit_into(to(X), to(y), to(n), 3, theta, n_hint=64)
+        torch.cuda.synchronize()
+        outs.append((theta.cpu().numpy(), f.raw.cpu().numpy(), f.mll.cpu().numpy(), f.iters.cpu().numpy(), f.last_launches))
+    live = n > 0
+    assert outs[0][4] == 1 and outs[1][4] > 20
+    assert np.array_equal(outs[0][3][live], outs[1][3][live])                 # iterations, evaluations
+    assert np.allclose(outs[0][1][live], outs[1][1][live], rtol=1e-12, atol=0)
+    assert np.allclose(outs[0][2][live], outs[1][2][live], rtol=1e-13, atol=0)
+    assert np.all(outs[0][0][~live] == 0)
