@@ -385,6 +385,42 @@ def bench_dpp(dev):
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1) / reps
         out[name] = {"sets": int(t.shape[0]), "ms": ms, "sets_per_s": t.shape[0] / (ms * 1e-3)}
+    # end to end at config-2 size: score + mean/std/z-score + stable sort + gather of the sorted sets
+    def e2e():
+        ld = ops.dpp_logdet_score(pool, idx, 1e-5)
+        stats, z = ops.dpp_zscore(ld)
+        zs, order = torch.sort(z, stable=True)
+        return pool[idx.long()[order]]
+    for _ in range(3):
+        e2e()
+    torch.cuda.synchronize(dev)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        e2e()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / 5
+    out["rank_n1e5"] = {"sets": 100000, "ms": ms, "sets_per_s": 1e5 / (ms * 1e-3), "what": "score + z-score + stable sort + gather"}
+    # FP64-pipe accounting of the scorer (k = 10): 45 pairs x (exp 22 + sqrt 15 + 8) + Cholesky 220 FMA + 10 x (sqrt 15 +
+    # div 14) + 10 x log 51 ~ 3045 DFMA-slots per set (profiles/fp64_peaks_r1.json slot costs)
+    out["fp64_pipe_frac_n1e7"] = out["n1e7"]["sets_per_s"] * 3045 * 2 / 1e12 / 36.6
+    # the reference's generate() path (un-rank + score + rank) at its own size, N = 10 000 (3.22 s in SURVEY.md §6)
+    import data_gen
+    d = data_gen.diverse_data_generator()
+    d.device = str(dev)
+    d.options["bounds"] = [(0, 100), (0, 100)]
+    d.options["N_samples"] = 10000
+    d.gamma = 1e-5
+    d.options["seed"] = 0
+    d.training_size = 10
+    d.options["time-debug"] = True
+    d.generate()
+    d.generate()
+    tt = d.tracker["time-tracking"]
+    out["generate_n1e4"] = {"seconds": tt["Total"], "host_rng_and_unrank_share": tt["sampling"], "scoring_share": tt["scoring"],
+                            "note": "element ranks are drawn by CPython/numpy generators exactly as the reference does (parity of "
+                                    "chosen sets); un-ranking, scoring, statistics and the sort run on the GPU"}
     # CPU: the oracle's twoD_score restatement (numpy slogdet), one core, bounded sample
     from oracle import dpp as odpp
     pool_h = pool.cpu().numpy()
