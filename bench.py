@@ -293,7 +293,9 @@ def run_b200(args):
                 "flops_model": "F_B = G (n^2 + 17 n + 30) per trial-iteration, exp/sqrt/erfc = 1 flop (SURVEY.md 8d)",
                 "kernel_share_of_step": kb_ms / ms_total if ms_total else None,
                 "gp_chol_share_of_step": ka_ms / ms_total if ms_total else None,
-                "launches_timed": len(kb)}
+                "launches_timed": len(kb),
+                "frac_by_n": {str(n): round(T * G * (n * n + 17 * n + 30) / (ms * 1e-3) / 1e12 / peak, 3)
+                              for n, ms in kb[:iters] if n in (10, 16, 24, 32, 48, 64, 80, 96, 109)}}
 
     if args.posterior == "incremental":
         # dominant kernel = grid_inc_kernel (+ the row append inside the same timed bracket): HBM-side model

@@ -76,9 +76,9 @@ extern "C" {
 int b200bo_bo_init(const double* y, int32_t* n, double* best_f, double* yall, int32_t* picked, int32_t* nit, int T,
                    int n_max, int max_iter, double tol, double optimal_y, void* stream) {
   using namespace b200bo;
-  if (!y || !n || !best_f || !yall || !picked || !nit) return arg_error("bo_init: null pointer");
   if (T < 0 || n_max < 1 || max_iter < 0) return arg_error("bo_init: bad sizes");
   if (T == 0) return 0;
+  if (!y || !n || !best_f || !yall || !picked || !nit) return arg_error("bo_init: null pointer");
   bo_init_kernel<<<(T + 127) / 128, 128, 0, as_stream(stream)>>>(y, n, best_f, yall, picked, nit, T, n_max, max_iter, tol, optimal_y);
   B200BO_CHECK_LAUNCH("bo_init");
   return 0;
@@ -88,10 +88,10 @@ int b200bo_bo_update(const double* grid, int G, const float* obj, const int32_t*
                      double* X, double* y, int32_t* n, double* best_f, double* yall, int32_t* picked, int32_t* nit,
                      int T, int n_max, int max_iter, int iter, double tol, double optimal_y, void* stream) {
   using namespace b200bo;
-  if (!grid || !obj || !surf_id || !arg_idx || !X || !y || !n || !best_f || !yall || !picked || !nit)
-    return arg_error("bo_update: null pointer");
   if (T < 0 || G < 1 || n_max < 1 || iter < 0 || iter >= max_iter) return arg_error("bo_update: bad sizes");
   if (T == 0) return 0;
+  if (!grid || !obj || !surf_id || !arg_idx || !X || !y || !n || !best_f || !yall || !picked || !nit)
+    return arg_error("bo_update: null pointer");
   bo_update_kernel<<<(T + 127) / 128, 128, 0, as_stream(stream)>>>(
       reinterpret_cast<const double2*>(grid), G, obj, surf_id, arg_idx, X, y, n, best_f, yall, picked, nit, T, n_max,
       max_iter, iter, tol, optimal_y);
@@ -101,8 +101,8 @@ int b200bo_bo_update(const double* grid, int G, const float* obj, const int32_t*
 
 int b200bo_bo_finalize(double* yall, const int32_t* nit, int32_t* n, int T, int max_iter, void* stream) {
   using namespace b200bo;
-  if (!yall || !nit || !n) return arg_error("bo_finalize: null pointer");
   if (T == 0) return 0;
+  if (!yall || !nit || !n) return arg_error("bo_finalize: null pointer");
   bo_finalize_kernel<<<(T + 127) / 128, 128, 0, as_stream(stream)>>>(yall, nit, n, T, max_iter);
   B200BO_CHECK_LAUNCH("bo_finalize");
   return 0;

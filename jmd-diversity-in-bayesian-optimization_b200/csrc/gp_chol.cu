@@ -513,10 +513,10 @@ int b200bo_gp_assemble_chol(const double* X, const double* y, const int32_t* n, 
                             double* Linv, double* alpha, double* logdet, double* wfrag, int32_t* status, int T,
                             int n_max, int n_hint, int kernel_id, void* stream) {
   using namespace b200bo;
-  if (!X || !y || !n || !theta) return arg_error("gp_assemble_chol: null input pointer");
   if (T < 0 || n_max < 1 || n_max > B200BO_NMAX) return arg_error("gp_assemble_chol: T=%d n_max=%d (max %d)", T, n_max, B200BO_NMAX);
   if (kernel_id < 0 || kernel_id > 3) return arg_error("gp_assemble_chol: kernel_id=%d", kernel_id);
   if (T == 0) return 0;
+  if (!X || !y || !n || !theta) return arg_error("gp_assemble_chol: null input pointer");
   return launch_chol(false, X, y, n, theta, L, Linv, alpha, logdet, wfrag, nullptr, nullptr, status, T, n_max, n_hint,
                      kernel_id, as_stream(stream));
 }
@@ -547,10 +547,10 @@ int b200bo_gp_fit(const double* X, const double* y, const int32_t* n, const doub
 int b200bo_mll_value_grad(const double* X, const double* y, const int32_t* n, const double* raw, double* value,
                           double* grad, int32_t* status, int T, int n_max, int n_hint, int kernel_id, void* stream) {
   using namespace b200bo;
-  if (!X || !y || !n || !raw || !value || !grad) return arg_error("mll_value_grad: null pointer");
   if (T < 0 || n_max < 1 || n_max > B200BO_NMAX) return arg_error("mll_value_grad: T=%d n_max=%d (max %d)", T, n_max, B200BO_NMAX);
   if (kernel_id < 0 || kernel_id > 3) return arg_error("mll_value_grad: kernel_id=%d", kernel_id);
   if (T == 0) return 0;
+  if (!X || !y || !n || !raw || !value || !grad) return arg_error("mll_value_grad: null pointer");
   return launch_chol(true, X, y, n, raw, nullptr, nullptr, nullptr, nullptr, nullptr, value, grad, status, T, n_max,
                      n_hint, kernel_id, as_stream(stream));
 }

@@ -214,9 +214,9 @@ int b200bo_wildcat_eval(const float* surf, const int32_t* surf_id, const double*
 int b200bo_wildcat_surface(const uint64_t* hseed, const int8_t* vecs, const double* peak_xy, const double* smooth,
                            const double* rug_amp, float* surf, int S, void* stream) {
   using namespace b200bo;
-  if (!hseed || !vecs || !peak_xy || !smooth || !rug_amp || !surf) return arg_error("wildcat_surface: null pointer");
   if (S < 0) return arg_error("wildcat_surface: S=%d", S);
   if (S == 0) return 0;
+  if (!hseed || !vecs || !peak_xy || !smooth || !rug_amp || !surf) return arg_error("wildcat_surface: null pointer");
   size_t smem = 2 * (size_t)WW_PTS * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(wildcat_surface_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e, "wildcat_surface: smem attribute");
@@ -230,9 +230,9 @@ int b200bo_wildcat_surface(const uint64_t* hseed, const int8_t* vecs, const doub
 
 int b200bo_simplex_noise(uint64_t hseed, const int8_t* vecs_h, const double* xy, double* out, long long M, void* stream) {
   using namespace b200bo;
-  if (!vecs_h || !xy || !out) return arg_error("simplex_noise: null pointer");
   if (M < 0) return arg_error("simplex_noise: M=%lld", M);
   if (M == 0) return 0;
+  if (!vecs_h || !xy || !out) return arg_error("simplex_noise: null pointer");
   long long blocks = (M + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   simplex_noise_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(

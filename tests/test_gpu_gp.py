@@ -293,3 +293,62 @@ def test_rank1_append_failure_is_handed_to_full_kernel():
     for t in range(2):
         _, alpha, _, so = ogp.gp_state(X[t, :4], y[t, :4], th[t], 3)
         assert np.allclose(al[t, :4].cpu().numpy(), alpha, rtol=1e-6, atol=1e-8 * np.abs(alpha).max())
+
+
+def test_edge_cases_empty_batch_inactive_trials_and_nonfinite(golden, lattice_grid):
+    from b200bo import ops, _lib
+    # empty batch: every entry is a no-op
+    e = lambda *shape, dt=torch.float64: torch.empty(shape, dtype=dt, device=DEV)
+    out = ops.gp_assemble_chol(e(0, 8, 2), e(0, 8), e(0, dt=torch.int32), e(0, 4), 3)
+    assert out["alpha"].shape == (0, 8)
+    r = ops.grid_posterior_acq_argmax(_to(lattice_grid[:64].copy()), e(0, 8, 2), e(0, ops.wfrag_doubles(8)), e(0, 8),
+                                      e(0, dt=torch.int32), e(0, 4), e(0), 3)
+    assert r["idx"].numel() == 0
+    # inactive trial (n = 0) between two live ones: skipped, idx -1, no status, neighbours untouched
+    n_max = 16
+    X, y, n, th = _make_batch(golden, lattice_grid, 3, [12], n_max, seed=4, theta=_theta())
+    n[1] = 0
+    st = ops.gp_assemble_chol(_to(X), _to(y), _to(n), _to(th), 3)
+    best = np.array([y[t, :12].max() for t in range(3)])
+    out = ops.grid_posterior_acq_argmax(_to(lattice_grid), _to(X), st["wfrag"], st["alpha"], _to(n), _to(th), _to(best), 3)
+    assert out["idx"][1].item() == -1 and out["status"][1].item() == 0
+    for t in (0, 2):
+        idx, _, _ = ogp.grid_step(lattice_grid, X[t, :12], y[t, :12], th[t], 3)
+        assert out["idx"][t].item() == idx
+    # a NaN observation poisons alpha -> every acquisition value is NaN: never wins, status says why
+    y2 = y.copy(); y2[0, 3] = np.nan
+    st = ops.gp_assemble_chol(_to(X), _to(y2), _to(n), _to(th), 3)
+    out = ops.grid_posterior_acq_argmax(_to(lattice_grid), _to(X), st["wfrag"], st["alpha"], _to(n), _to(th), _to(best), 3)
+    assert out["idx"][0].item() == -1
+    assert out["status"][0].item() & ogp.ST_NONFINITE and out["status"][0].item() & ogp.ST_ALL_MASKED
+    assert out["idx"][2].item() >= 0 and out["status"][2].item() == 0
+    # argument errors are reported, nothing is launched
+    with pytest.raises(_lib.B200boError):
+        ops.gp_assemble_chol(e(1, 200, 2), e(1, 200), torch.ones(1, dtype=torch.int32, device=DEV), e(1, 4), 3)   # n_max > 128
+    with pytest.raises(_lib.B200boError):
+        ops.gp_assemble_chol(_to(X), _to(y), _to(n), _to(th), 9)                                                    # bad kernel id
+    with pytest.raises(_lib.B200boError):
+        ops.grid_posterior_acq_argmax(_to(lattice_grid), _to(X), st["wfrag"], st["alpha"], _to(n), _to(th), _to(best), 3,
+                                      acq_id=ops.UCB, acq_param=-1.0)
+    assert "UCB" in _lib.load().b200bo_last_error_string().decode()
+
+
+def test_ragged_n_inside_one_launch(golden, lattice_grid):
+    """Trials with very different n in one launch (lattice kernel: template sized by the largest, ragged body for the rest)."""
+    from b200bo import ops
+    n_max = 104
+    X, y, n, th = _make_batch(golden, lattice_grid, 6, [104, 9, 57, 1, 33, 96], n_max, seed=31, theta=_theta())
+    st = ops.gp_assemble_chol(_to(X), _to(y), _to(n), _to(th), 3)
+    best = np.array([y[t, :n[t]].max() for t in range(6)])
+    grid = _to(lattice_grid)
+    lat = ops.Lattice.from_points(grid)
+    ktab = ops.kernel_table(_to(th[:1]), 3, lat)
+    out = ops.grid_posterior_acq_argmax_lattice(lat, ktab, None, _to(X), st["wfrag"], st["alpha"], _to(n), _to(th), _to(best), 3, debug=True)
+    for t in range(6):
+        idx, val, sto, mu, var, a = ogp.grid_step(lattice_grid, X[t, :n[t]], y[t, :n[t]], th[t], 3, return_fields=True)
+        assert np.allclose(out["mu"][t].cpu().numpy(), mu, rtol=1e-8, atol=1e-8 * np.abs(mu).max())
+        assert np.allclose(out["var"][t].cpu().numpy(), var, rtol=1e-8, atol=1e-10 * th[t, 2])
+        assert out["idx"][t].item() == idx
+    # a too-small n_hint must not corrupt anything: flagged, idx -1
+    out = ops.grid_posterior_acq_argmax_lattice(lat, ktab, None, _to(X), st["wfrag"], st["alpha"], _to(n), _to(th), _to(best), 3, n_hint=40)
+    assert out["idx"][0].item() == -1 and out["idx"][1].item() >= 0 and out["idx"][4].item() >= 0
