@@ -26,41 +26,45 @@ namespace b200bo {
 
 __host__ __device__ constexpr int slot_of(int a, int b) { return a * (a + 1) / 2 + b; }
 
-// k(r) / s and (d k / d ell) / s from the cached distance (RBF caches r^2). Operation order as common.cuh.
-__device__ __forceinline__ void kern_pair(int kid, double dc, double ell, double a_scale, double& kl, double& dk) {
-  if (kid == B200BO_KERNEL_RBF) {
-    double q = dc / (ell * ell);
-    double e = exp(dc * a_scale);
-    kl = e;
-    dk = q * exp(-0.5 * q) / ell;
-  } else if (kid == B200BO_KERNEL_MATERN12) {
-    double d = dc / ell;
-    double e = exp(-d);
-    kl = e;
-    dk = d * e / ell;
-  } else if (kid == B200BO_KERNEL_MATERN32) {
-    double a = a_scale * dc;
-    double e = exp(-a);
-    kl = (1.0 + a) * e;
-    dk = (a * a) * e / ell;
-  } else {
-    double a = a_scale * dc;
-    double e = exp(-a);
-    kl = (1.0 + a + (a * a) / 3.0) * e;
-    dk = ((a * a) / 3.0) * (1.0 + a) * e / ell;
-  }
+// Kernel value and derivative from the cached distance dc (RBF caches r^2). Every kind is poly(a) * exp(-a), so the
+// unrolled per-entry code holds ONE inlined exp whatever the kind (code size is what bounds this kernel's
+// instruction fetch). Values are bit-identical to kernel_from_r2 (common.cuh), i.e. to the matrix K-A factorises.
+__device__ __forceinline__ double kern_arg(int kid, double dc, double ell, double a_scale) {
+  if (kid == B200BO_KERNEL_RBF) return -(dc * a_scale);
+  if (kid == B200BO_KERNEL_MATERN12) return dc / ell;
+  return a_scale * dc;
 }
 
 __device__ __forceinline__ double kern_only(int kid, double dc, double s, double ell, double a_scale) {
-  if (kid == B200BO_KERNEL_RBF) return s * exp(dc * a_scale);
-  if (kid == B200BO_KERNEL_MATERN12) return s * exp(-(dc / ell));
-  double a = a_scale * dc;
-  if (kid == B200BO_KERNEL_MATERN32) return s * ((1.0 + a) * exp(-a));
-  return s * ((1.0 + a + (a * a) / 3.0) * exp(-a));
+  const double a = kern_arg(kid, dc, ell, a_scale);
+  const double e = exp(-a);
+  if (kid == B200BO_KERNEL_MATERN32) return s * ((1.0 + a) * e);
+  if (kid == B200BO_KERNEL_MATERN52) return s * ((1.0 + a + (a * a) / 3.0) * e);
+  return s * e;
+}
+
+// kl = k / s ; dk = (d k / d ell) * ell / s   (the common factor s / ell is applied once to the reduced sum)
+__device__ __forceinline__ void kern_pair(int kid, double dc, double ell, double a_scale, double& kl, double& dk) {
+  const double a = kern_arg(kid, dc, ell, a_scale);
+  const double e = exp(-a);
+  if (kid == B200BO_KERNEL_RBF) {
+    kl = e;
+    dk = (2.0 * a) * e;                      // q = r^2 / l^2 = 2 a
+  } else if (kid == B200BO_KERNEL_MATERN12) {
+    kl = e;
+    dk = a * e;
+  } else if (kid == B200BO_KERNEL_MATERN32) {
+    kl = (1.0 + a) * e;
+    dk = (a * a) * e;
+  } else {
+    kl = (1.0 + a + (a * a) / 3.0) * e;
+    dk = ((a * a) / 3.0) * (1.0 + a) * e;
+  }
 }
 
 struct FitSmem {
   double* dist;    // NS * FT   cached distances, [slot][thread]
+  double* kbuf;    // NS * FT   per-entry staging between the runtime transcendental loops and the register tile
   double* vbuf;    // 2 * (NP + 2) pivot column (double buffered), [NP] = 1 / pivot
   double* alpha;   // NP  (alpha[NP-1] = -r^T Khat^-1 r)
   double* dpiv;    // NP  pivots
@@ -71,7 +75,7 @@ struct FitSmem {
 
 template <int NB, int OW>
 __host__ __device__ constexpr size_t fit_smem_doubles() {
-  return (size_t)(NB * (NB + 1) / 2) * (OW * OW) + 2 * (OW * NB + 2) + 5 * (OW * NB);
+  return (size_t)(NB * (NB + 1)) * (OW * OW) + 2 * (OW * NB + 2) + 5 * (OW * NB);
 }
 
 template <int NB, int OW>
@@ -79,7 +83,8 @@ __device__ __forceinline__ FitSmem fit_carve(double* sm) {
   constexpr int NS = NB * (NB + 1) / 2, NP = OW * NB, FT = OW * OW;
   FitSmem s;
   s.dist = sm;
-  s.vbuf = s.dist + (size_t)NS * FT;
+  s.kbuf = s.dist + (size_t)NS * FT;
+  s.vbuf = s.kbuf + (size_t)NS * FT;
   s.alpha = s.vbuf + 2 * (NP + 2);
   s.dpiv = s.alpha + NP;
   s.xs = s.dpiv + NP;
@@ -105,24 +110,25 @@ __device__ __forceinline__ void fit_params_from_raw(const double* raw, int kerne
   p.lp_const = lp_const;
 }
 
-// cache pairwise distances of the owned entries (sqrt(r2); r2 itself for RBF)
+// cache pairwise distances of the owned entries (sqrt(r2); r2 itself for RBF). Runtime loop over the slots: the
+// transcendental code exists once, not once per slot.
 template <int NB, int OW>
 __device__ __forceinline__ void fit_cache_dist(const FitSmem& s, int n, int kernel_id) {
-  constexpr int FT = OW * OW;
+  constexpr int NS = NB * (NB + 1) / 2, FT = OW * OW;
   const int tid = threadIdx.x, tr = tid / OW, tc = tid % OW;
-#pragma unroll
-  for (int a = 0; a < NB; ++a)
-#pragma unroll
-    for (int b = 0; b <= a; ++b) {
-      const int r = tr + OW * a, c = tc + OW * b;
-      double v = 0.0;
-      if (r < n && c <= r) {
-        double dx = s.xs[r] - s.xs[c], dy = s.ys[r] - s.ys[c];
-        double r2 = dx * dx + dy * dy;
-        v = kernel_id == B200BO_KERNEL_RBF ? r2 : sqrt(r2);
-      }
-      s.dist[(size_t)slot_of(a, b) * FT + tid] = v;
+  int a = 0, b = 0;
+#pragma unroll 1
+  for (int sl = 0; sl < NS; ++sl) {
+    const int r = tr + OW * a, c = tc + OW * b;
+    double v = 0.0;
+    if (r < n && c <= r) {
+      double dx = s.xs[r] - s.xs[c], dy = s.ys[r] - s.ys[c];
+      double r2 = dx * dx + dy * dy;
+      v = kernel_id == B200BO_KERNEL_RBF ? r2 : sqrt(r2);
     }
+    s.dist[(size_t)sl * FT + tid] = v;
+    if (++b > a) { b = 0; ++a; }
+  }
 }
 
 // One evaluation of value and gradient at the parameters in `par` (shared memory, read by every thread).
@@ -142,26 +148,31 @@ __device__ __forceinline__ void mll_eval_sweep(const FitSmem& s, int n, int kern
     if (attempt > 0) st |= B200BO_ST_JITTER;
     __syncthreads();                       // previous users of vbuf / alpha are done
     // ---- assemble the owned entries: Khat (lower), augmented row NP-1 = y - c
-#pragma unroll
-    for (int a = 0; a < NB; ++a)
-#pragma unroll
-      for (int b = 0; b <= a; ++b) {
+    {
+      int a = 0, b = 0;
+#pragma unroll 1
+      for (int sl = 0; sl < NS; ++sl) {       // runtime loop: one copy of the exp code
         const int r = tr + OW * a, c = tc + OW * b;
         double v = 0.0;
         if (r < n && c <= r) {
-          v = kern_only(kernel_id, s.dist[(size_t)slot_of(a, b) * FT + tid], sc, ell, a_scale);
+          v = kern_only(kernel_id, s.dist[(size_t)sl * FT + tid], sc, ell, a_scale);
           if (r == c) v += noise + jitter;
-        } else if (a == NB - 1 && tr == OW - 1 && c < n) {
+        } else if (r == NP - 1 && c < n) {
           v = s.yv[c] - cst;
         }
-        A[slot_of(a, b)] = v;
+        s.kbuf[(size_t)sl * FT + tid] = v;
+        if (++b > a) { b = 0; ++a; }
       }
+    }
+#pragma unroll
+    for (int sl = 0; sl < NS; ++sl) A[sl] = s.kbuf[(size_t)sl * FT + tid];     // own writes: no barrier needed
     // ---- sweep pivots 0..n-1
     ok = true;
     int buf = 0;
 #pragma unroll
     for (int kb = 0; kb < NB; ++kb) {
       const int kt_end = min(OW, n - OW * kb);
+#pragma unroll 1
       for (int kt = 0; kt < kt_end; ++kt) {
         const int k = OW * kb + kt;
         double* v = s.vbuf + buf * (NP + 2);
@@ -238,16 +249,29 @@ __device__ __forceinline__ void mll_eval_sweep(const FitSmem& s, int n, int kern
 #pragma unroll
     for (int b = 0; b <= a; ++b) {
       const int r = tr + OW * a, c = tc + OW * b;
+      double wa = 0.0;
       if (r < n && c <= r) {
         const double a_rc = fma(ar[a], ac[b], A[slot_of(a, b)]);
-        double kl, dk;
-        kern_pair(kernel_id, s.dist[(size_t)slot_of(a, b) * FT + tid], ell, a_scale, kl, dk);
-        const double w = (c == r) ? 1.0 : 2.0;        // symmetric: (r,c) and (c,r)
         if (c == r) q2 += a_rc;
-        q3 = fma(w * a_rc, kl, q3);
-        q4 = fma(w * a_rc, sc * dk, q4);
+        wa = (c == r) ? a_rc : 2.0 * a_rc;            // symmetric: (r,c) and (c,r)
       }
+      s.kbuf[(size_t)slot_of(a, b) * FT + tid] = wa;
     }
+  {
+    int a = 0, b = 0;
+#pragma unroll 1
+    for (int sl = 0; sl < NS; ++sl) {         // runtime loop: one copy of the exp code
+      const int r = tr + OW * a, c = tc + OW * b;
+      if (r < n && c <= r) {
+        double kl, dk;
+        kern_pair(kernel_id, s.dist[(size_t)sl * FT + tid], ell, a_scale, kl, dk);
+        const double wa = s.kbuf[(size_t)sl * FT + tid];
+        q3 = fma(wa, kl, q3);
+        q4 = fma(wa, dk, q4);
+      }
+      if (++b > a) { b = 0; ++a; }
+    }
+  }
   double q[5] = {q1, q2, q3, q4, q5};
 #pragma unroll
   for (int m = 0; m < 5; ++m) {
@@ -271,7 +295,7 @@ __device__ __forceinline__ void mll_eval_sweep(const FitSmem& s, int n, int kern
     out[1] = (0.5 * tsum[1] + (a_prior - 1.0) / noise - rate) / nn;
     out[2] = tsum[0] / nn;
     out[3] = 0.5 * tsum[2] * par->sig_s / nn;
-    out[4] = 0.5 * tsum[3] * par->sig_l / nn;
+    out[4] = 0.5 * (tsum[3] * (sc / ell)) * par->sig_l / nn;
     *st_out = st;
   }
   __syncthreads();
