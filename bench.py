@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--cpu-trials-per-core", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dpp", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the secondary configs[2]/configs[3] figures")
     ap.add_argument("--posterior", default="full", choices=["full", "incremental"],
                     help="full: O(n^2) fused recomputation per iteration (headline, north-star kernel); incremental: "
                          "O(n) rank-1 posterior update per candidate with (mu, var) state in HBM")
@@ -352,6 +353,8 @@ def run_b200(args):
         del bo2
     if rank == 0 and world == 1 and not args.no_dpp:
         line["dpp"] = bench_dpp(dev)
+    if rank == 0 and world == 1 and not args.no_configs:
+        line["other_configs"] = bench_other_configs(dev, surf, S)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         v, its, wall = cpu_sample(cores, args.cpu_trials_per_core, n0, iters)
@@ -363,6 +366,83 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as td
         td.destroy_process_group()
+
+
+def bench_other_configs(dev, surf, S):
+    """Secondary figures (not the headline): BASELINE configs[2] (per-iteration hyper-parameter fit, 1 000 trials) and
+    configs[3] (200 x 200 lattice, fixed theta; a 1 184-trial slice of the 10 000), plus the bootstrap of a
+    (1000 x 102) curve matrix (results.py:787-794)."""
+    import torch
+    from b200bo import engine, fit, ops
+    out = {}
+    rng = np.random.default_rng(99)
+
+    def run(name, lat, T, iters, theta, tol, reps=1):
+        G = lat.G
+        pts = lat.points(dev)
+        if lat.h == 1.0:
+            obj = surf[:, :100, :100].reshape(S, G).contiguous()
+        else:
+            sidx = torch.arange(S, dtype=torch.int32, device=dev).repeat_interleave(G)
+            obj = ops.wildcat_eval(surf.reshape(S, 101, 101), pts.repeat(S, 1), sidx).reshape(S, G).float().contiguous()
+        idx = torch.as_tensor(np.stack([rng.choice(G, 10, replace=False) for _ in range(T)]), device=dev)
+        sid = torch.as_tensor((np.arange(T) % S).astype(np.int32), device=dev)
+        X0 = pts[idx]
+        y0 = obj[sid.long()[:, None], idx].double()
+        fitter = None if theta is not None else fit.LBFGSFitter(T, dev)
+        bo = engine.BatchedBO(pts, obj, sid, X0, y0, iters, theta=theta, tol=tol, fitter=fitter, lattice=lat)
+        bo.run()                                                   # warm-up
+        torch.cuda.synchronize(dev)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            bo.reset(X0, y0)
+            res = bo.run()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        sec = e0.elapsed_time(e1) * 1e-3 / reps
+        nit = int(res.nit.sum().item())
+        out[name] = {"trials": T, "grid": f"{lat.Gx}x{lat.Gy}", "iterations_max": iters, "tol": tol, "seconds": sec,
+                     "bo_iterations": nit, "bo_iterations_per_s": nit / sec, "status_bits": int(res.status.max().item())}
+        if fitter is not None:
+            out[name]["fit_evaluations_mean_last"] = float(fitter.iters[:, 1].float().mean().item())
+
+    theta = torch.tensor(THETA, dtype=torch.float64, device=dev)
+    run("configs[2]_fit_every_iteration_tol_disabled", ops.Lattice(100, 100), 1000, 100, None, -1.0)
+    run("configs[2]_fit_every_iteration_tol_0.1", ops.Lattice(100, 100), 1000, 100, None, 0.1)
+    run("configs[3]_grid200_fixed_theta_slice", ops.Lattice(200, 200, 0.0, 0.0, 0.5), 1184, 100, theta, -1.0)
+    # bootstrap of a (1000 trials x 102) gap-curve matrix, 1000 replicates; the oracle restatement timed on a slice
+    import random
+    import utils
+    from oracle import bootstrap as ob
+    data = np.maximum.accumulate(rng.uniform(0, 100, size=(1000, 102)), axis=1)[:, ::-1].copy()
+    random.seed(0)
+    idx = torch.as_tensor(ob.draw_indices(1000, 1000), device=dev)
+    dd = torch.as_tensor(data, device=dev)
+    for _ in range(2):
+        ops.bootstrap_ci(dd, idx)
+    torch.cuda.synchronize(dev)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        ops.bootstrap_ci(dd, idx)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / 5
+    t0 = time.perf_counter()
+    random.seed(0)
+    utils.bootstrap(data, trials=1000, device=str(dev))
+    t_api = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    random.seed(0)
+    ob.bootstrap(data[:, :4], trials=50)
+    t_cpu = (time.perf_counter() - t0) * (102 / 4) * (1000 / 50)
+    out["bootstrap_1000x102_1000_replicates"] = {"kernels_ms": ms, "gathered_GB_per_s": 1000 * 1000 * 102 * 8 / (ms * 1e-3) / 1e9,
+                                                 "api_seconds_incl_host_index_draws": t_api,
+                                                 "cpu_port_seconds_extrapolated": t_cpu,
+                                                 "cpu_sample": "oracle restatement of utils.bootstrap on 4 of 102 columns x 50 of "
+                                                               "1000 replicates, scaled linearly, 1 core"}
+    return out
 
 
 def bench_dpp(dev):

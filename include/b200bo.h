@@ -210,6 +210,18 @@ int b200bo_gp_fit(const double* X, const double* y, const int32_t* n, const doub
                   int n_max, int n_hint, int kernel_id, double lb_noise, double gtol, double ftol, int max_iter,
                   int max_ls, int max_rounds, void* stream);
 
+/* ---- bootstrap statistics of gap curves ------------------------------
+ * replaces utils.bootstrap (Src/utils.py:39-115; callers results.py:172-184,787-802).
+ * data (N,C) f64 row-major = N trials x C positions (C = 1 for a vector of cumulative gaps);
+ * idx (B,N) int32 = for replicate b, the rows drawn by random.choices (the host draws them from CPython's
+ * generator, so the replicates are the reference's); boot (B,C) out: boot[b][c] = np.mean of the drawn rows at
+ * position c with numpy's 1-D pairwise summation order (bit-identical to the reference's list means). */
+int b200bo_bootstrap_means(const double* data, int N, int C, const int32_t* idx, int B, double* boot, void* stream);
+/* per column of boot (B,C): out (1+nq, C) = { np.mean over the B replicates (pairwise),
+ * np.percentile(100 q[0]), ... } with numpy's default "linear" interpolation; q (nq) f64 DEVICE = percent / 100.
+ * B <= 16384 (one CTA sorts a column in shared memory); a column containing NaN yields NaN percentiles. */
+int b200bo_column_mean_percentiles(const double* boot, int B, int C, const double* q, int nq, double* out, void* stream);
+
 /* ---- batched BO loop bookkeeping (one thread per trial) ---------------------------
  * replaces the Python statements between two acquisitions in BOloop / BOloop_fixparam:
  * objective look-up (Src/BO.py:104), append (:164-165), yopt / yall.append (:168-169),

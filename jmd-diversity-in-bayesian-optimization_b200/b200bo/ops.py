@@ -447,3 +447,21 @@ def bo_finalize(yall, nit, n, max_iter):
     lib = _lib.load()
     T = nit.numel()
     check(lib.b200bo_bo_finalize(_ptr(yall), _ptr(nit), _ptr(n), T, int(max_iter), _stream()), "bo_finalize")
+
+
+def bootstrap_ci(data: torch.Tensor, idx: torch.Tensor, percentiles=(2.5, 97.5)) -> torch.Tensor:
+    """utils.bootstrap on device: data (N,C) f64, idx (B,N) int32 resampled rows -> (1 + len(percentiles), C) f64 =
+    [mean over replicates, percentile...] of the replicate means (numpy summation order / "linear" percentiles)."""
+    data = _cu(data, torch.float64, "data")
+    idx = _cu(idx, torch.int32, "idx")
+    N, C = data.shape
+    B = idx.shape[0]
+    if idx.shape[1] != N:
+        raise ValueError("idx must be (B, N)")
+    boot = torch.empty((B, C), dtype=torch.float64, device=data.device)
+    check(_lib.load().b200bo_bootstrap_means(_ptr(data), N, C, _ptr(idx), B, _ptr(boot), _stream()), "bootstrap_means")
+    q = torch.tensor([float(p) / 100 for p in percentiles], dtype=torch.float64, device=data.device)   # np.true_divide(q, 100)
+    out = torch.empty((1 + len(percentiles), C), dtype=torch.float64, device=data.device)
+    check(_lib.load().b200bo_column_mean_percentiles(_ptr(boot), B, C, _ptr(q), len(percentiles), _ptr(out), _stream()),
+          "column_mean_percentiles")
+    return out

@@ -193,11 +193,29 @@ def gen_author_data():
         json.dump(rows, fh, indent=1)
 
 
+def gen_bootstrap():
+    """utils.bootstrap (Src/utils.py:39-115) on gap-curve shaped inputs, seeded through the global generator."""
+    ut = refshim.load("utils")
+    rng = np.random.default_rng(5)
+    out = {}
+    # (N trials, D positions) monotone gap curves like results.opt_gap, and a vector like cum_opt_gap
+    curves = np.maximum.accumulate(rng.uniform(0, 100, size=(37, 12)), axis=1)[:, ::-1].copy()
+    big = rng.normal(50, 20, size=(300, 5))                       # N > 128: exercises the pairwise split
+    vec = rng.gamma(2.0, 100.0, size=41)
+    for name, data, trials, seed in (("curves", curves, 200, 11), ("big", big, 64, 12), ("vec", vec, 150, 13)):
+        random.seed(seed)
+        out[f"{name}_data"] = data
+        out[f"{name}_trials"] = np.array([trials, seed])
+        out[f"{name}_ci"] = np.asarray(ut.bootstrap(data if name != "curves" else [row for row in data], trials=trials))
+    np.savez_compressed(os.path.join(HERE, "bootstrap.npz"), **out)
+
+
 if __name__ == "__main__":
     gen_simplex()
     gen_wildcat()
     gen_combinadics()
     gen_dpp()
     gen_author_data()
+    gen_bootstrap()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

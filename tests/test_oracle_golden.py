@@ -195,3 +195,16 @@ def test_psd_safe_cholesky_levels():
     assert st == ogp.ST_JITTER and np.all(np.isfinite(L))
     L, st = ogp.chol_safe(-np.eye(3))
     assert st == (ogp.ST_JITTER | ogp.ST_CHOL_FAIL)
+
+
+def test_bootstrap_oracle_matches_reference_vectors(golden):
+    """oracle/bootstrap.py vs the reference's own utils.bootstrap (tests/golden/bootstrap.npz): bit-exact."""
+    import random
+    from oracle import bootstrap as ob
+    g = golden("bootstrap.npz")
+    for name in ("curves", "big", "vec"):
+        trials, seed = (int(v) for v in g[f"{name}_trials"])
+        random.seed(seed)
+        ci = ob.bootstrap(g[f"{name}_data"], trials)
+        assert ci.shape == g[f"{name}_ci"].shape
+        assert np.array_equal(ci, g[f"{name}_ci"])
