@@ -210,6 +210,21 @@ int b200bo_gp_fit(const double* X, const double* y, const int32_t* n, const doub
                   int n_max, int n_hint, int kernel_id, double lb_noise, double gtol, double ftol, int max_iter,
                   int max_ls, int max_rounds, void* stream);
 
+/* ---- K-C for large training sets -------------------------------------
+ * replaces fit_gpytorch_model on the 1 010 ... 1 209-point models of the hyper-parameter extraction experiment
+ * (Scripts/Experiment3-2-1.py:63-87: HPextract -> BO.initialize_model(nu=1.5) -> fit_gpytorch_model).
+ * Same objective, gradient and optimiser as b200bo_gp_fit / b200bo_mll_value_grad, for n[t] <= n_max <= 4000: one
+ * fit per CTA, the matrix lives in the caller's workspace (b200bo_gp_fit_large_workspace_bytes(T, n_max) bytes),
+ * blocked symmetric sweep with a register-tiled rank-64 update. X (T,n_max,2), y (T,n_max), n (T). */
+size_t b200bo_gp_fit_large_workspace_bytes(int T, int n_max);
+int b200bo_gp_fit_large(const double* X, const double* y, const int32_t* n, const double* raw0, int raw0_per_trial,
+                        double* theta_out, double* raw_out, double* mll_out, int32_t* iters_out, int32_t* status, int T,
+                        int n_max, int kernel_id, double lb_noise, double gtol, double ftol, int max_iter, int max_ls,
+                        int max_rounds, void* ws, size_t ws_bytes, void* stream);
+int b200bo_mll_value_grad_large(const double* X, const double* y, const int32_t* n, const double* raw, double* value,
+                                double* grad, int32_t* status, int T, int n_max, int kernel_id, void* ws, size_t ws_bytes,
+                                void* stream);
+
 /* ---- bootstrap statistics of gap curves ------------------------------
  * replaces utils.bootstrap (Src/utils.py:39-115; callers results.py:172-184,787-802).
  * data (N,C) f64 row-major = N trials x C positions (C = 1 for a vector of cumulative gaps);

@@ -104,6 +104,10 @@ def fit_gpytorch_model(mll, device="cuda:0"):
     X = m.train_x.to(dev).reshape(1, n, 2).contiguous()
     y = m.train_obj.to(dev).reshape(1, n).contiguous()
     nn = torch.tensor([n], dtype=torch.int32, device=dev)
+    if n >= fit.LARGE_N:          # Experiment3-2-1.py:63-72 fits 1 010 ... 1 209 points: blocked K-C (csrc/gp_fit_large.cu)
+        r = fit.fit_large(X, y, nn, m.kernel_id, raw0=tuple(m.raw()))
+        m.set_raw(r["raw"][0].cpu().numpy())
+        return mll
     f = fit.LBFGSFitter(1, dev, raw0=tuple(m.raw()))
     theta = torch.empty((1, 4), dtype=torch.float64, device=dev)
     f.fit_into(X, y, nn, m.kernel_id, theta)

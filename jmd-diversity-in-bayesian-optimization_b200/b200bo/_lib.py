@@ -49,6 +49,10 @@ PROTOTYPES = {
     "b200bo_lbfgs_step": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_double, c_double, c_double, c_int, c_int, P]),
     "b200bo_gp_fit": (c_int, [P, P, P, P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int, c_double, c_double, c_double,
                               c_int, c_int, c_int, P]),
+    "b200bo_gp_fit_large_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "b200bo_gp_fit_large": (c_int, [P, P, P, P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_double, c_double, c_double,
+                                    c_int, c_int, c_int, P, c_size_t, P]),
+    "b200bo_mll_value_grad_large": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, P, c_size_t, P]),
     "b200bo_bootstrap_means": (c_int, [P, c_int, c_int, P, c_int, P, P]),
     "b200bo_column_mean_percentiles": (c_int, [P, c_int, c_int, P, c_int, P, P]),
     "b200bo_bo_init": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_double, c_double, P]),

@@ -79,3 +79,40 @@ class LBFGSFitter:
         self.last_launches = launches
         self.last_rounds = rounds
         return theta_out
+
+
+LARGE_N = 128          # observation counts above the in-register K-C kernels (B200BO_NMAX) take the blocked path
+
+
+def mll_value_grad_large(X, y, n, raw, kernel_id, status=None):
+    """K-C for n up to 4000 (csrc/gp_fit_large.cu): X (T,n_max,2), y (T,n_max), n (T) i32, raw (T,4) ->
+    value (T), grad (T,4)."""
+    lib = _lib.load()
+    p, s = ops._ptr, ops._stream()
+    T, n_max = y.shape
+    ws = torch.empty(int(lib.b200bo_gp_fit_large_workspace_bytes(T, n_max)), dtype=torch.uint8, device=X.device)
+    value = torch.empty(T, dtype=torch.float64, device=X.device)
+    grad = torch.empty((T, 4), dtype=torch.float64, device=X.device)
+    check(lib.b200bo_mll_value_grad_large(p(X), p(y), p(n), p(raw), p(value), p(grad), p(status), T, n_max, int(kernel_id),
+                                          p(ws), ws.numel(), s), "mll_value_grad_large")
+    return value, grad
+
+
+def fit_large(X, y, n, kernel_id, raw0=DEFAULT_RAW, gtol=1e-5, ftol=2.220446049250313e-9, max_iter=200, max_ls=30,
+              max_rounds=600, status=None):
+    """Fit T large models (one CTA each) from ``raw0``; returns dict(theta, raw, mll, iters) of device tensors.
+    The batched counterpart of Experiment3-2-1.py's HPextract fan-out (one fit per ipyparallel engine there)."""
+    lib = _lib.load()
+    p, s = ops._ptr, ops._stream()
+    dev = X.device
+    T, n_max = y.shape
+    ws = torch.empty(int(lib.b200bo_gp_fit_large_workspace_bytes(T, n_max)), dtype=torch.uint8, device=dev)
+    r0 = torch.as_tensor(raw0, dtype=torch.float64, device=dev).contiguous()
+    theta = torch.zeros((T, 4), dtype=torch.float64, device=dev)
+    raw = torch.zeros((T, 4), dtype=torch.float64, device=dev)
+    mll = torch.zeros(T, dtype=torch.float64, device=dev)
+    iters = torch.zeros((T, 2), dtype=torch.int32, device=dev)
+    check(lib.b200bo_gp_fit_large(p(X), p(y), p(n), p(r0), 1 if r0.dim() == 2 else 0, p(theta), p(raw), p(mll), p(iters),
+                                  p(status), T, n_max, int(kernel_id), NOISE_LB, float(gtol), float(ftol), int(max_iter),
+                                  int(max_ls), int(max_rounds), p(ws), ws.numel(), s), "gp_fit_large")
+    return {"theta": theta, "raw": raw, "mll": mll, "iters": iters}
