@@ -24,6 +24,16 @@ from Combination import combination_finder
 from b200bo import host, ops
 
 
+def set_diff2d(A, B):
+    """Rows of the larger of two (m,2) arrays that do not occur in the smaller one, in their original order
+    (data_gen.py:59-66)."""
+    A = np.asarray(A); B = np.asarray(B)
+    if len(A) < len(B):
+        A, B = B, A
+    hit = (A[:, None] == B).all(-1).any(-1)
+    return A[~hit]
+
+
 class diverse_data_generator:
     def __init__(self):
         self.acquiredsets = []
@@ -265,6 +275,15 @@ class diverse_data_generator:
                 print("Only Poorly coorelated gammas could be found for the given range of gamma(s).")
                 return
         return pairs[np.abs([np.abs(p)[0] - np.abs(p)[1] for p in pairs]).argmax()]
+
+
+    def optgammarand(self, current_set, set_size):
+        """`set_size` random pool points not in `current_set` (data_gen.py:844-851): the growing training sets of the
+        hyper-parameter extraction experiment (Experiment3-2-1.py:296-305)."""
+        random.seed(self.options["seed"])
+        if self.X is None:
+            self.constructX()
+        return np.array(random.sample(list(set_diff2d(current_set, self.X)), set_size))
 
 
 class random_data_generator:

@@ -210,6 +210,35 @@ def gen_bootstrap():
     np.savez_compressed(os.path.join(HERE, "bootstrap.npz"), **out)
 
 
+def gen_hp_extract():
+    """hp_series.extract_hyperparam (Src/results.py:342-392) on synthetic hyper-parameter samples; np.random seeded."""
+    res = refshim.load("results")
+    out = {}
+    for seed in (0, 1, 2):
+        rng = np.random.default_rng(seed)
+        data = {"likelihood.noise_covar.raw_noise": np.abs(rng.normal(2e-3, 5e-4, 400)),
+                "mean_module.raw_constant": np.concatenate([rng.normal(40, 1.5, 300), rng.normal(60, 1.0, 280)]),
+                "covar_module.raw_outputscale": np.concatenate([rng.normal(190, 8, 350), rng.normal(120, 3, 40)]),
+                "covar_module.base_kernel.raw_lengthscale": rng.gamma(20, 0.5, 500)}
+        h = res.hp_series.__new__(res.hp_series)          # hp_series.__init__ trips over its setter-less property
+        h.data = data
+        np.random.seed(seed)
+        import types
+        had = sys.modules.get("utils")
+        sys.modules["utils"] = types.SimpleNamespace(bootstrap=None)     # extract_hyperparam imports it and never uses it
+        try:
+            with quiet():
+                h.extract_hyperparam()
+        finally:
+            if had is None:
+                del sys.modules["utils"]
+            else:
+                sys.modules["utils"] = had
+        out[str(seed)] = {"data": {k: v.tolist() for k, v in data.items()}, "optdict": {k: np.asarray(v).tolist() for k, v in h.optdict.items()}}
+    with open(os.path.join(HERE, "hp_extract.json"), "w") as fh:
+        json.dump(out, fh)
+
+
 if __name__ == "__main__":
     gen_simplex()
     gen_wildcat()
@@ -217,5 +246,6 @@ if __name__ == "__main__":
     gen_dpp()
     gen_author_data()
     gen_bootstrap()
+    gen_hp_extract()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

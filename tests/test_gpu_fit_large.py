@@ -96,3 +96,41 @@ def test_fit_gpytorch_model_dispatches_large_models(golden):
     v0 = ogp.mll_value_grad(tx.numpy().astype(np.float64), ty.numpy().reshape(-1).astype(np.float64), [2, 0, 0, 0], 2)[0]
     v1 = ogp.mll_value_grad(tx.numpy().astype(np.float64), ty.numpy().reshape(-1).astype(np.float64), raw, 2)[0]
     assert v1 > v0 and raw[0] >= 1e-4
+
+
+def test_hp_extract_pipeline_like_experiment3_2_1(golden):
+    """Experiment3-2-1.py:296-320 at reduced size: growing training sets -> one fit each -> hp_series -> modes."""
+    import data_gen
+    import objectives
+    import results
+    from b200bo import hpextract
+    synth = objectives.objectives()
+    synth.bounds = [(0, 100), (0, 100)]
+    synth.seed = 0
+    synth.args = {"N": 1, "Smoothness": 0.4, "rug_freq": 1, "rug_amp": 0.4}
+    f = synth.generate_cont()
+    d = data_gen.diverse_data_generator()
+    d.options["bounds"] = synth.bounds
+    d.options["N_samples"] = 2000
+    d.options["seed"] = 4
+    d.gamma = 1e-5
+    d.training_size = 10
+    d.generate()
+    init = d.sample(95)
+    rand = d.optgammarand(init, 160)
+    sets = [np.concatenate([init, rand[:m]]) for m in range(130, 160)]        # 140 ... 169 points
+    hps = hpextract.hp_extract_batched(sets, f)
+    assert len(hps) == 30 and all(h.hyperparameters is not None for h in hps)
+    assert all(set(h.hyperparameters) == set(hpextract.PARAM_NAMES) for h in hps)
+    series = results.hp_series()
+    series.data = hps
+    series.updateres()
+    assert all(len(v) == 30 for v in series.data.values())
+    assert np.all(series.data["likelihood.noise_covar.raw_noise"] >= 1e-4 - 1e-18)
+    # the fitted optimum is a maximiser: compare one set against the oracle's value at the defaults
+    X = sets[0]; Y = np.asarray(f(X), dtype=np.float32).astype(np.float64)
+    raw = [series.data[k][0] for k in hpextract.PARAM_NAMES]
+    assert ogp.mll_value_grad(X, Y, raw, 2)[0] > ogp.mll_value_grad(X, Y, [2.0, 0.0, 0.0, 0.0], 2)[0]
+    np.random.seed(0)
+    series.extract_hyperparam()
+    assert set(series.optdict) >= set(hpextract.PARAM_NAMES) and all(len(v) >= 1 for v in series.optdict.values())

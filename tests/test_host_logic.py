@@ -193,3 +193,28 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "bo_iterations_per_s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_extract_hyperparam_matches_reference_golden(golden):
+    """results.hp_series.extract_hyperparam vs the reference's own output (tests/golden/hp_extract.json)."""
+    import results
+    g = golden("hp_extract.json")
+    for seed, case in g.items():
+        h = results.hp_series()
+        h.data = {k: np.array(v) for k, v in case["data"].items()}
+        np.random.seed(int(seed))
+        h.extract_hyperparam()
+        assert set(h.optdict) == set(case["optdict"])
+        for k, v in case["optdict"].items():
+            assert np.array_equal(h.optdict[k], np.array(v)), (seed, k)
+
+
+def test_hp_series_updateres_fills_failed_fits():
+    import results
+    s = results.hp_series()
+    for i, v in enumerate([1.0, None, 3.0, None, None]):
+        r = results.hp_result()
+        r.hyperparameters = None if v is None else {"a": [v], "b": [10 * v]}
+        s.data.append(r)
+    s.updateres()
+    assert s.data["a"].tolist() == [1.0, 1.0, 3.0, 3.0, 3.0] and s.getkeys() == ["a", "b"]
