@@ -213,7 +213,7 @@ int b200bo_gp_fit(const double* X, const double* y, const int32_t* n, const doub
 /* ---- K-C for large training sets -------------------------------------
  * replaces fit_gpytorch_model on the 1 010 ... 1 209-point models of the hyper-parameter extraction experiment
  * (Scripts/Experiment3-2-1.py:63-87: HPextract -> BO.initialize_model(nu=1.5) -> fit_gpytorch_model).
- * Same objective, gradient and optimiser as b200bo_gp_fit / b200bo_mll_value_grad, for n[t] <= n_max <= 4000: one
+ * Same objective, gradient and optimiser as b200bo_gp_fit / b200bo_mll_value_grad, for n[t] <= n_max <= 8192: one
  * fit per CTA, the matrix lives in the caller's workspace (b200bo_gp_fit_large_workspace_bytes(T, n_max) bytes),
  * blocked symmetric sweep with a register-tiled rank-64 update. X (T,n_max,2), y (T,n_max), n (T). */
 size_t b200bo_gp_fit_large_workspace_bytes(int T, int n_max);

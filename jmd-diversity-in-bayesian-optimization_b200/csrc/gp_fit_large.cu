@@ -13,8 +13,9 @@
 //     A[i,K] = P_i,  A[K,K] = S
 // which is what 64 consecutive single-pivot sweeps compose to. After all blocks A = -Khat^-1; pivots give log|Khat|.
 // Rows n .. npad-1 are padded with the identity (pivot 1, no coupling), so every block is a full block.
-// The rank-64 update is a register-tiled FP64 GEMM: 64 x 64 output tile per CTA pass, 4 x 4 per thread, operands
-// staged in shared memory in k-pair-major order so one LDS.128 feeds two FMAs per output.
+// The rank-64 update runs on the FP64 MMA path (mma.sync.m8n8k4.f64, as K-B): 64 x 64 output tile per CTA pass, a warp
+// owns 8 rows x 64 columns (eight independent DMMA chains), operands staged in shared memory (9 LDS.64 per 8 DMMA).
+// (A first version with a 4 x 4 DFMA register tile was shared-memory bound at 21 % of the FP64 pipe.)
 //
 // Roofline: FP64 pipe (n^3/2 FMA per evaluation; 0.89 GFMA at n = 1210); matrix traffic 2 * 8 * npad^2/2 B per block
 // step, i.e. npad/64 sweeps over an 5.9 MB triangle per evaluation (mostly L2-resident per SM-local fit).
@@ -24,7 +25,7 @@ namespace b200bo {
 
 constexpr int LGB = 64;            // pivot block / tile edge
 constexpr int LGT = 256;           // threads: 16 x 16 owners, 4 x 4 entries of a tile each
-constexpr int LG_NMAX = 4096;
+constexpr int LG_NMAX = 8192;
 
 struct LargePar {
   double noise, cst, sc, ell, a_scale, sig_s, sig_l, lp_const;
@@ -57,13 +58,13 @@ __device__ __forceinline__ void large_kern_pair(int kid, double r2, double ell, 
 
 struct LargeCtx {
   double* A;        // (npad, ld) lower triangle, row-major
-  double* Vt;       // (nblk, 32, 64, 2) panel before the update, k-pair-major per 64-row block
-  double* Pt;       // (nblk, 32, 64, 2) panel after
+  double* Vt;       // (nblk, 64, 64) panel before the update, one dense [row][k] tile per 64-row block
+  double* Pt;       // (nblk, 64, 64) panel after
   double* dpiv;     // (npad) pivots
-  double2* B0;      // shared: 32 x 64 double2 tile
-  double2* B1;
-  double2* Ss;      // shared: S = -D^-1 (k-pair-major, full symmetric)
-  double* xs;       // shared (npad)
+  double* B0;       // shared: 64 x 64 operand tile, row-major [row][k], leading dimension LDT
+  double* B1;
+  double* Ss;       // shared: S = -D^-1, full symmetric, same layout
+  double* xs;       // workspace (npad): L1/L2-cached, keeps shared memory at three tiles so two fits share an SM
   double* ys;
   double* res;      // y - c
   double* alpha;
@@ -71,30 +72,48 @@ struct LargeCtx {
   int n, npad, nblk, ld;
 };
 
-// acc[a][b] -= sum_k P[r][k] V[c][k],  r = tr + 16 a, c = tc + 16 b; operands k-pair-major: T2[k2 * 64 + row] = (k, k+1)
-__device__ __forceinline__ void tile_mma(double (&acc)[4][4], const double2* __restrict__ P2, const double2* __restrict__ V2,
-                                         int tr, int tc) {
+constexpr int LDT = 68;            // operand tile leading dimension: each half-warp of a fragment load hits 16 banks pairs
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// acc -= P V^T on the FP64 MMA path. Warp w owns rows 8w .. 8w+7 of the 64 x 64 tile and all eight 8-column tiles
+// (eight independent DMMA chains); lane l holds C[8w + l/4][8j + 2(l%4) + {0,1}]. Per 4-wide k-block: one A fragment
+// (P[row][k], negated) feeds eight DMMAs, each with its own B fragment (V[col][k]) — 9 LDS.64 per 8 DMMA.
+__device__ __forceinline__ void tile_mma(double (&acc)[8][2], const double* __restrict__ Ps, const double* __restrict__ Vs,
+                                         int warp, int lane) {
+  const double* pa = Ps + (8 * warp + (lane >> 2)) * LDT + (lane & 3);
+  const double* pb = Vs + (lane >> 2) * LDT + (lane & 3);
 #pragma unroll 4
-  for (int k2 = 0; k2 < LGB / 2; ++k2) {
-    double2 p[4], v[4];
+  for (int kb = 0; kb < LGB / 4; ++kb) {
+    const double a = -pa[4 * kb];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) p[a] = P2[k2 * LGB + tr + 16 * a];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) v[b] = V2[k2 * LGB + tc + 16 * b];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        acc[a][b] = fma(-p[a].x, v[b].x, acc[a][b]);
-        acc[a][b] = fma(-p[a].y, v[b].y, acc[a][b]);
-      }
+    for (int j = 0; j < 8; ++j) dmma_m8n8k4(acc[j][0], acc[j][1], a, pb[j * 8 * LDT + 4 * kb]);
   }
 }
 
-__device__ __forceinline__ void tile_copy_in(double2* dst, const double* __restrict__ src) {   // 32 KB straight copy
-  const double2* s2 = reinterpret_cast<const double2*>(src);
-  for (int e = threadIdx.x; e < LGB * LGB / 2; e += LGT) dst[e] = s2[e];
+__device__ __forceinline__ void tile_copy_in(double* dst, const double* __restrict__ src) {   // dense 64 x 64 -> padded
+  for (int e = threadIdx.x; e < LGB * LGB / 2; e += LGT) {
+    const int r = e >> 5, k = (e & 31) * 2;
+    const double2 v = *reinterpret_cast<const double2*>(src + r * LGB + k);
+    *reinterpret_cast<double2*>(dst + r * LDT + k) = v;
+  }
 }
+
+// same copy through cp.async (16 B per request, L2 -> shared memory without staging in registers): the next operand
+// tile streams in behind the DMMAs of the current one
+__device__ __forceinline__ void tile_copy_in_async(double* dst, const double* __restrict__ src) {
+  for (int e = threadIdx.x; e < LGB * LGB / 2; e += LGT) {
+    const int r = e >> 5, k = (e & 31) * 2;
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst + r * LDT + k);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src + r * LGB + k));
+  }
+  asm volatile("cp.async.commit_group;\n" ::);
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // full symmetric sweep of a 64 x 64 tile held as T[a][b] <-> (tr + 16 a, tc + 16 b); returns false on pivot <= 0
 __device__ __forceinline__ bool sweep_tile(double (&T)[4][4], double* vbuf, double* dpiv_out, int tr, int tc) {
@@ -194,75 +213,89 @@ __device__ void large_eval(const LargeCtx& cx, int kernel_id, const LargePar* pa
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           const int r = tr + 16 * a, c = tc + 16 * b;          // S[r][c]; as operand V2[k = r][col = c]
-          reinterpret_cast<double*>(cx.Ss)[((r >> 1) * LGB + c) * 2 + (r & 1)] = T[a][b];
+          cx.Ss[c * LDT + r] = T[a][b];                       // B operand V[col = c][k = r] = S[r][c]
           if (c <= r) cx.A[(size_t)(k0 + r) * ld + k0 + c] = T[a][b];
         }
       __syncthreads();
       // ---- panel: V_I (old) and P_I = V_I D^-1 for every other row block
+      const int warp = tid >> 5, lane = tid & 31;
+      const int mr = 8 * warp + (lane >> 2), mc = 2 * (lane & 3);        // this lane's row / first column in a tile
       for (int I = 0; I < nblk; ++I) {
         if (I == K) continue;
-        double* b0 = reinterpret_cast<double*>(cx.B0);
         if (I > K) {
           for (int e = tid; e < LGB * LGB; e += LGT) {
             const int r = e >> 6, k = e & 63;
-            b0[((k >> 1) * LGB + r) * 2 + (k & 1)] = cx.A[(size_t)(I * LGB + r) * ld + k0 + k];
+            cx.B0[r * LDT + k] = cx.A[(size_t)(I * LGB + r) * ld + k0 + k];
           }
         } else {
           for (int e = tid; e < LGB * LGB; e += LGT) {
             const int k = e >> 6, r = e & 63;
-            b0[((k >> 1) * LGB + r) * 2 + (k & 1)] = cx.A[(size_t)(k0 + k) * ld + I * LGB + r];
+            cx.B0[r * LDT + k] = cx.A[(size_t)(k0 + k) * ld + I * LGB + r];
           }
         }
         __syncthreads();
         {
-          double2* vt = reinterpret_cast<double2*>(cx.Vt + (size_t)I * LGB * LGB);
-          for (int e = tid; e < LGB * LGB / 2; e += LGT) vt[e] = cx.B0[e];
+          double* vt = cx.Vt + (size_t)I * LGB * LGB;
+          for (int e = tid; e < LGB * LGB; e += LGT) vt[e] = cx.B0[(e >> 6) * LDT + (e & 63)];
         }
-        double acc[4][4];
+        double acc[8][2];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-        tile_mma(acc, cx.B0, cx.Ss, tr, tc);                     // -V S = V D^-1
+        for (int j = 0; j < 8; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
+        tile_mma(acc, cx.B0, cx.Ss, warp, lane);                   // -V S = V D^-1
         double* pt = cx.Pt + (size_t)I * LGB * LGB;
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const int r = tr + 16 * a, c = tc + 16 * b;
-            pt[((c >> 1) * LGB + r) * 2 + (c & 1)] = acc[a][b];
-            if (I > K) cx.A[(size_t)(I * LGB + r) * ld + k0 + c] = acc[a][b];
-            else cx.A[(size_t)(k0 + c) * ld + I * LGB + r] = acc[a][b];
+        for (int j = 0; j < 8; ++j) {
+          const int c = 8 * j + mc;
+          *reinterpret_cast<double2*>(pt + mr * LGB + c) = make_double2(acc[j][0], acc[j][1]);
+          if (I > K) {
+            *reinterpret_cast<double2*>(cx.A + (size_t)(I * LGB + mr) * ld + k0 + c) = make_double2(acc[j][0], acc[j][1]);
+          } else {
+            cx.A[(size_t)(k0 + c) * ld + I * LGB + mr] = acc[j][0];
+            cx.A[(size_t)(k0 + c + 1) * ld + I * LGB + mr] = acc[j][1];
           }
+        }
         __syncthreads();
       }
-      // ---- rank-64 update of every tile outside row / column block K
+      // ---- rank-64 update of every tile outside row / column block K. The V_J operand tiles are double-buffered
+      //      (B1 and the S buffer, which is idle in this phase) and prefetched with cp.async.
       for (int I = 0; I < nblk; ++I) {
         if (I == K) continue;
-        tile_copy_in(cx.B0, cx.Pt + (size_t)I * LGB * LGB);
-        for (int J = 0; J <= I; ++J) {
-          if (J == K) continue;
-          tile_copy_in(cx.B1, cx.Vt + (size_t)J * LGB * LGB);
-          __syncthreads();
-          double acc[4][4];
+        __syncthreads();                                   // everyone is done with B0 / the operand buffers
+        tile_copy_in_async(cx.B0, cx.Pt + (size_t)I * LGB * LGB);
+        int J = (K == 0) ? 1 : 0;                          // first J != K (J <= I always has one: J = I)
+        tile_copy_in_async(cx.B1, cx.Vt + (size_t)J * LGB * LGB);
+        int cur = 0;
+        while (J <= I) {
+          int Jn = J + 1;
+          if (Jn == K) ++Jn;
+          cp_async_wait_all();
+          __syncthreads();                                 // tile J landed; the other buffer is free again
+          double* vcur = cur ? cx.Ss : cx.B1;
+          if (Jn <= I) tile_copy_in_async(cur ? cx.B1 : cx.Ss, cx.Vt + (size_t)Jn * LGB * LGB);
+          double acc[8][2];
+          double* arow = cx.A + (size_t)(I * LGB + mr) * ld + J * LGB + mc;
 #pragma unroll
-          for (int a = 0; a < 4; ++a)
+          for (int j = 0; j < 8; ++j) {
+            const double2 v = *reinterpret_cast<const double2*>(arow + 8 * j);    // above the diagonal: discarded below
+            acc[j][0] = v.x; acc[j][1] = v.y;
+          }
+          tile_mma(acc, cx.B0, vcur, warp, lane);
+          if (I != J) {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              const int r = I * LGB + tr + 16 * a, c = J * LGB + tc + 16 * b;
-              acc[a][b] = c <= r ? cx.A[(size_t)r * ld + c] : 0.0;
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<double2*>(arow + 8 * j) = make_double2(acc[j][0], acc[j][1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = 8 * j + mc;
+              if (c <= mr) arow[8 * j] = acc[j][0];
+              if (c + 1 <= mr) arow[8 * j + 1] = acc[j][1];
             }
-          tile_mma(acc, cx.B0, cx.B1, tr, tc);
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              const int r = I * LGB + tr + 16 * a, c = J * LGB + tc + 16 * b;
-              if (c <= r) cx.A[(size_t)r * ld + c] = acc[a][b];
-            }
-          __syncthreads();
+          }
+          J = Jn;
+          cur ^= 1;
         }
       }
+      __syncthreads();
     }
   }
   if (!ok) {
@@ -341,7 +374,7 @@ __device__ void large_eval(const LargeCtx& cx, int kernel_id, const LargePar* pa
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(LGT, 1)
+__global__ void __launch_bounds__(LGT, 2)
 gp_fit_large_kernel(const double* __restrict__ X, const double* __restrict__ y, const int32_t* __restrict__ n_arr,
                     const double* __restrict__ raw0, int raw0_per_trial, int eval_only, double* __restrict__ theta_out,
                     double* __restrict__ raw_out, double* __restrict__ mll_out, double* __restrict__ grad_out,
@@ -365,15 +398,14 @@ gp_fit_large_kernel(const double* __restrict__ X, const double* __restrict__ y, 
   cx.Vt = cx.A + (size_t)npad_max * npad_max;
   cx.Pt = cx.Vt + (size_t)npad_max * LGB;
   cx.dpiv = cx.Pt + (size_t)npad_max * LGB;
-  cx.B0 = sm2;
-  cx.B1 = cx.B0 + LGB * LGB / 2;
-  cx.Ss = cx.B1 + LGB * LGB / 2;
-  double* sd = reinterpret_cast<double*>(cx.Ss + LGB * LGB / 2);
-  cx.xs = sd;
+  cx.B0 = reinterpret_cast<double*>(sm2);
+  cx.B1 = cx.B0 + LGB * LDT;
+  cx.Ss = cx.B1 + LGB * LDT;
+  cx.vbuf = cx.Ss + LGB * LDT;
+  cx.xs = cx.dpiv + npad_max;
   cx.ys = cx.xs + npad_max;
   cx.res = cx.ys + npad_max;
   cx.alpha = cx.res + npad_max;
-  cx.vbuf = cx.alpha + npad_max;
   __shared__ double red[(LGT / 32) * 6];
   __shared__ double out[5];
   __shared__ LargePar par;
@@ -432,7 +464,7 @@ gp_fit_large_kernel(const double* __restrict__ X, const double* __restrict__ y, 
 
 static size_t large_ws_doubles_per_fit(int n_max) {
   const size_t npad = (size_t)((n_max + LGB - 1) / LGB) * LGB;
-  return npad * npad + 2 * npad * LGB + npad;
+  return npad * npad + 2 * npad * LGB + 5 * npad;
 }
 
 static int launch_large(const double* X, const double* y, const int32_t* n, const double* raw0, int raw0_per_trial,
@@ -447,7 +479,7 @@ static int launch_large(const double* X, const double* y, const int32_t* n, cons
   if (ws_bytes < per_fit * sizeof(double) * (size_t)T) return arg_error("%s: workspace too small (%zu < %zu)", what, ws_bytes,
                                                                            per_fit * sizeof(double) * (size_t)T);
   const int npad = ((n_max + LGB - 1) / LGB) * LGB;
-  const size_t smem = 3 * (size_t)LGB * LGB * sizeof(double) + (4 * (size_t)npad + 2 * (LGB + 2)) * sizeof(double);
+  const size_t smem = 3 * (size_t)LGB * LDT * sizeof(double) + 2 * (LGB + 2) * sizeof(double);
   if (smem > 227 * 1024) return arg_error("%s: n_max=%d needs %zu B shared memory", what, n_max, smem);
   cudaError_t e = cudaFuncSetAttribute(gp_fit_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e, what);
