@@ -35,18 +35,19 @@ __device__ __forceinline__ double kern_arg(int kid, double dc, double ell, doubl
   return a_scale * dc;
 }
 
-__device__ __forceinline__ double kern_only(int kid, double dc, double s, double ell, double a_scale) {
-  const double a = kern_arg(kid, dc, ell, a_scale);
-  const double e = exp(-a);
+__device__ __forceinline__ double kern_from_exp(int kid, double a, double e, double s) {
   if (kid == B200BO_KERNEL_MATERN32) return s * ((1.0 + a) * e);
   if (kid == B200BO_KERNEL_MATERN52) return s * ((1.0 + a + (a * a) / 3.0) * e);
   return s * e;
 }
 
-// kl = k / s ; dk = (d k / d ell) * ell / s   (the common factor s / ell is applied once to the reduced sum)
-__device__ __forceinline__ void kern_pair(int kid, double dc, double ell, double a_scale, double& kl, double& dk) {
+__device__ __forceinline__ double kern_only(int kid, double dc, double s, double ell, double a_scale) {
   const double a = kern_arg(kid, dc, ell, a_scale);
-  const double e = exp(-a);
+  return kern_from_exp(kid, a, exp(-a), s);
+}
+
+// kl = k / s ; dk = (d k / d ell) * ell / s   (the common factor s / ell is applied once to the reduced sum)
+__device__ __forceinline__ void kern_pair_from_exp(int kid, double a, double e, double& kl, double& dk) {
   if (kid == B200BO_KERNEL_RBF) {
     kl = e;
     dk = (2.0 * a) * e;                      // q = r^2 / l^2 = 2 a
@@ -62,9 +63,15 @@ __device__ __forceinline__ void kern_pair(int kid, double dc, double ell, double
   }
 }
 
+__device__ __forceinline__ void kern_pair(int kid, double dc, double ell, double a_scale, double& kl, double& dk) {
+  const double a = kern_arg(kid, dc, ell, a_scale);
+  kern_pair_from_exp(kid, a, exp(-a), kl, dk);
+}
+
 struct FitSmem {
   double* dist;    // NS * FT   cached distances, [slot][thread]
   double* kbuf;    // NS * FT   per-entry staging between the runtime transcendental loops and the register tile
+  double* ebuf;    // NS * FT   exp(-a) of the current parameters (variants with room: the gradient traces reuse it)
   double* vbuf;    // 2 * (NP + 2) pivot column (double buffered), [NP] = 1 / pivot
   double* alpha;   // NP  (alpha[NP-1] = -r^T Khat^-1 r)
   double* dpiv;    // NP  pivots
@@ -73,9 +80,13 @@ struct FitSmem {
   double* yv;      // NP
 };
 
+// keep exp(-a) per entry between the assembly and the gradient traces where it does not cost occupancy
+template <int NB, int OW>
+__host__ __device__ constexpr bool fit_ecache() { return OW == 8 ? NB <= 6 : (NB == 7 || NB == 8); }
+
 template <int NB, int OW>
 __host__ __device__ constexpr size_t fit_smem_doubles() {
-  return (size_t)(NB * (NB + 1)) * (OW * OW) + 2 * (OW * NB + 2) + 5 * (OW * NB);
+  return (size_t)(NB * (NB + 1) / 2) * (OW * OW) * (fit_ecache<NB, OW>() ? 3 : 2) + 2 * (OW * NB + 2) + 5 * (OW * NB);
 }
 
 template <int NB, int OW>
@@ -84,7 +95,8 @@ __device__ __forceinline__ FitSmem fit_carve(double* sm) {
   FitSmem s;
   s.dist = sm;
   s.kbuf = s.dist + (size_t)NS * FT;
-  s.vbuf = s.kbuf + (size_t)NS * FT;
+  s.ebuf = s.kbuf + (size_t)NS * FT;
+  s.vbuf = s.ebuf + (fit_ecache<NB, OW>() ? (size_t)NS * FT : 0);
   s.alpha = s.vbuf + 2 * (NP + 2);
   s.dpiv = s.alpha + NP;
   s.xs = s.dpiv + NP;
@@ -155,7 +167,19 @@ __device__ __forceinline__ void mll_eval_sweep(const FitSmem& s, int n, int kern
         const int r = tr + OW * a, c = tc + OW * b;
         double v = 0.0;
         if (r < n && c <= r) {
-          v = kern_only(kernel_id, s.dist[(size_t)sl * FT + tid], sc, ell, a_scale);
+          if (fit_ecache<NB, OW>()) {
+            if (attempt == 0) {
+              const double a = kern_arg(kernel_id, s.dist[(size_t)sl * FT + tid], ell, a_scale);
+              const double e = exp(-a);
+              s.ebuf[(size_t)sl * FT + tid] = e;
+              v = kern_from_exp(kernel_id, a, e, sc);
+            } else {
+              const double a = kern_arg(kernel_id, s.dist[(size_t)sl * FT + tid], ell, a_scale);
+              v = kern_from_exp(kernel_id, a, s.ebuf[(size_t)sl * FT + tid], sc);
+            }
+          } else {
+            v = kern_only(kernel_id, s.dist[(size_t)sl * FT + tid], sc, ell, a_scale);
+          }
           if (r == c) v += noise + jitter;
         } else if (r == NP - 1 && c < n) {
           v = s.yv[c] - cst;
@@ -264,7 +288,12 @@ __device__ __forceinline__ void mll_eval_sweep(const FitSmem& s, int n, int kern
       const int r = tr + OW * a, c = tc + OW * b;
       if (r < n && c <= r) {
         double kl, dk;
-        kern_pair(kernel_id, s.dist[(size_t)sl * FT + tid], ell, a_scale, kl, dk);
+        if (fit_ecache<NB, OW>()) {
+          const double a = kern_arg(kernel_id, s.dist[(size_t)sl * FT + tid], ell, a_scale);
+          kern_pair_from_exp(kernel_id, a, s.ebuf[(size_t)sl * FT + tid], kl, dk);
+        } else {
+          kern_pair(kernel_id, s.dist[(size_t)sl * FT + tid], ell, a_scale, kl, dk);
+        }
         const double wa = s.kbuf[(size_t)sl * FT + tid];
         q3 = fma(wa, kl, q3);
         q4 = fma(wa, dk, q4);
