@@ -467,6 +467,22 @@ def bench_dpp(dev):
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1) / reps
         out[name] = {"sets": int(t.shape[0]), "ms": ms, "sets_per_s": t.shape[0] / (ms * 1e-3)}
+    # lattice-table variant (what data_gen.generate() uses on the constructX pool): bit-identical scores
+    table = ops.dpp_table(lat, 1e-5, dev)
+    for name, t in (("lattice_n1e5", idx), ("lattice_n1e7", big)):
+        for _ in range(3):
+            ops.dpp_logdet_score_lattice(lat, table, t)
+        torch.cuda.synchronize(dev)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            ops.dpp_logdet_score_lattice(lat, table, t)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / 5
+        out[name] = {"sets": int(t.shape[0]), "ms": ms, "sets_per_s": t.shape[0] / (ms * 1e-3)}
+    out["lattice_identical_to_generic"] = bool(torch.equal(ops.dpp_logdet_score_lattice(lat, table, idx),
+                                                           ops.dpp_logdet_score(pool, idx, 1e-5)))
     # end to end at config-2 size: score + mean/std/z-score + stable sort + gather of the sorted sets
     def e2e():
         ld = ops.dpp_logdet_score(pool, idx, 1e-5)

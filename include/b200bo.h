@@ -63,6 +63,14 @@ long long b200bo_fp64_fma_probe(double* out, int blocks, int iters, void* stream
 int b200bo_dpp_logdet_score(const double* pool, int pool_size, const int32_t* idx, long long N, int k,
                             double gamma, double* logdet, void* stream);
 
+/* Lattice variant of K-D: the pool is the constructX lattice (Src/data_gen.py:294-303), node g <-> (g % Gx, g / Gx),
+ * x = x0 + h ix with coordinates on which differences are exact (integers or dyadic steps), so an entry of the
+ * L-ensemble depends on (|dx|, |dy|) only and is read from table (Gy,Gx) f64 built by b200bo_dpp_table for this gamma
+ * (same arithmetic as the generic kernel: values bit-identical). k <= 12; idx (N,k) int32 flat node indices. */
+int b200bo_dpp_table(int Gx, int Gy, double h, double gamma, double* table, void* stream);
+int b200bo_dpp_logdet_score_lattice(const double* table, int Gx, int Gy, const int32_t* idx, long long N, int k,
+                                    double* logdet, void* stream);
+
 /* mean / population-sd / z-scores of the scoring block of sub_dpp, data_gen.py:406-408.
  * stats (2) f64 out = {mean, sd}; z (N) f64 out; ws: >= b200bo_dpp_stats_workspace_bytes(N). */
 size_t b200bo_dpp_stats_workspace_bytes(long long N);

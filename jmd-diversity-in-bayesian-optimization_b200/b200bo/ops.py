@@ -65,6 +65,43 @@ def dpp_logdet_score(pool: torch.Tensor, idx: torch.Tensor, gamma: float) -> tor
     return out
 
 
+def dpp_lattice_of(pool) -> "Lattice | None":
+    """The constructX lattice behind a pool, if it is one whose coordinate differences are exact in fp64 (all
+    coordinates multiples of 2^-20 below 2^30 — integer or dyadic steps), else None: only then does an L-ensemble
+    entry depend on (|dx|, |dy|) alone bit for bit."""
+    import numpy as np
+    g = pool.detach().cpu().numpy() if isinstance(pool, torch.Tensor) else np.asarray(pool)
+    lat = Lattice.from_points(g)
+    if lat is None:
+        return None
+    scaled = g * 2.0 ** 20
+    if not (np.all(scaled == np.round(scaled)) and np.abs(g).max() < 2.0 ** 30):
+        return None
+    return lat
+
+
+def dpp_table(lat: "Lattice", gamma: float, device) -> torch.Tensor:
+    """(Gy,Gx) f64 table of exp(-gamma (sqrt(dx^2+dy^2))^2) over lattice offsets — the entries K-D would compute."""
+    out = torch.empty((lat.Gy, lat.Gx), dtype=torch.float64, device=device)
+    check(_lib.load().b200bo_dpp_table(lat.Gx, lat.Gy, float(lat.h), float(gamma), _ptr(out), _stream()), "dpp_table")
+    return out
+
+
+def dpp_logdet_score_lattice(lat: "Lattice", table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """Lattice variant of dpp_logdet_score: idx (N,k<=12) int32 flat node indices -> (N,) f64, bit-identical values."""
+    _cu(table, torch.float64, "table")
+    _cu(idx, torch.int32, "idx")
+    if idx.dim() != 2 or table.shape != (lat.Gy, lat.Gx):
+        raise _lib.B200boError("dpp_logdet_score_lattice: idx must be (N,k), table (Gy,Gx)")
+    N, k = idx.shape
+    out = torch.empty(N, dtype=torch.float64, device=idx.device)
+    if N == 0:
+        return out
+    check(_lib.load().b200bo_dpp_logdet_score_lattice(_ptr(table), lat.Gx, lat.Gy, _ptr(idx), N, k, _ptr(out), _stream()),
+          "dpp_logdet_score_lattice")
+    return out
+
+
 def dpp_zscore(logdet: torch.Tensor):
     """(mean, sd) as a (2,) tensor and z-scores — data_gen.py:406-408."""
     lib = _lib.load()

@@ -65,6 +65,69 @@ dpp_logdet_reg_kernel(const double2* __restrict__ pool, const int32_t* __restric
   out[i] = ok ? acc : nan("");
 }
 
+// ---- lattice variant ------------------------------------------------------------------------------------
+// The reference's pool is always the constructX lattice (data_gen.py:294-303): an entry of the L-ensemble depends
+// on (|dx|, |dy|) only, so it is looked up in a (Gy, Gx) table (80 KB for 100 x 100: L1-resident) built once per
+// gamma by the same dpp_entry() code — bit-identical values, ~75 FP64-pipe instructions (sqrt + exp) replaced by
+// one gather per pair. What is left per set is the 10 x 10 Cholesky + 10 logs.
+__global__ void __launch_bounds__(256)
+dpp_table_kernel(int Gx, int Gy, double h, double neg_gamma, double* __restrict__ table) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= Gx * Gy) return;
+  const int dy = e / Gx, dx = e - dy * Gx;
+  table[e] = (dx | dy) ? dpp_entry(h * dx, h * dy, 0.0, 0.0, neg_gamma) : 1.0;
+}
+
+template <int K>
+__global__ void __launch_bounds__(128)
+dpp_logdet_lattice_kernel(const double* __restrict__ table, int Gx, int G, const int32_t* __restrict__ idx, long long N,
+                          double* __restrict__ out) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  int ix[K], iy[K];
+  const int32_t* row = idx + i * K;
+  bool ok = true;
+#pragma unroll
+  for (int a = 0; a < K; ++a) {
+    const int g = row[a];
+    ok = ok && g >= 0 && g < G;
+    const int gg = ok ? g : 0;
+    iy[a] = gg / Gx;
+    ix[a] = gg - iy[a] * Gx;
+  }
+  double A[K * (K + 1) / 2];
+#pragma unroll
+  for (int r = 0; r < K; ++r) {
+#pragma unroll
+    for (int c = 0; c < r; ++c) A[r * (r + 1) / 2 + c] = __ldg(&table[abs(iy[r] - iy[c]) * Gx + abs(ix[r] - ix[c])]);
+    A[r * (r + 1) / 2 + r] = 1.0;
+  }
+  double acc = 0.0;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    double d = A[j * (j + 1) / 2 + j];
+    ok = ok && (d > 0.0);
+    acc += log(d);
+    double inv = 1.0 / sqrt(d);
+#pragma unroll
+    for (int r = j + 1; r < K; ++r) A[r * (r + 1) / 2 + j] *= inv;
+#pragma unroll
+    for (int c = j + 1; c < K; ++c) {
+      double lcj = A[c * (c + 1) / 2 + j];
+#pragma unroll
+      for (int r = c; r < K; ++r) A[r * (r + 1) / 2 + c] = fma(-A[r * (r + 1) / 2 + j], lcj, A[r * (r + 1) / 2 + c]);
+    }
+  }
+  out[i] = ok ? acc : nan("");
+}
+
+template <int K>
+static void launch_lattice(const double* table, int Gx, int G, const int32_t* idx, long long N, double* out, cudaStream_t st) {
+  const int threads = 128;
+  const long long blocks = (N + threads - 1) / threads;
+  dpp_logdet_lattice_kernel<K><<<(unsigned)blocks, threads, 0, st>>>(table, Gx, G, idx, N, out);
+}
+
 // generic k: one set per CTA, full matrix in shared memory (k*k doubles).
 __global__ void __launch_bounds__(128)
 dpp_logdet_smem_kernel(const double2* __restrict__ pool, const int32_t* __restrict__ idx, long long N, int k,
@@ -191,6 +254,44 @@ static void launch_reg(const double* pool, const int32_t* idx, long long N, doub
 }  // namespace b200bo
 
 extern "C" {
+
+int b200bo_dpp_table(int Gx, int Gy, double h, double gamma, double* table, void* stream) {
+  using namespace b200bo;
+  if (Gx < 1 || Gy < 1 || !(h > 0.0)) return arg_error("dpp_table: Gx=%d Gy=%d h=%g", Gx, Gy, h);
+  if (!table) return arg_error("dpp_table: null pointer");
+  const int total = Gx * Gy;
+  dpp_table_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(Gx, Gy, h, -gamma, table);
+  B200BO_CHECK_LAUNCH("dpp_table");
+  return 0;
+}
+
+int b200bo_dpp_logdet_score_lattice(const double* table, int Gx, int Gy, const int32_t* idx, long long N, int k,
+                                    double* logdet, void* stream) {
+  using namespace b200bo;
+  if (Gx < 1 || Gy < 1 || k < 1 || k > KREG_MAX || N < 0)
+    return arg_error("dpp_logdet_score_lattice: Gx=%d Gy=%d k=%d (max %d) N=%lld", Gx, Gy, k, KREG_MAX, N);
+  if (N == 0) return 0;
+  if (!table || !idx || !logdet) return arg_error("dpp_logdet_score_lattice: null pointer");
+  if (N > 2147483647LL * 128) return arg_error("dpp_logdet_score_lattice: N too large");
+  cudaStream_t st = as_stream(stream);
+  const int G = Gx * Gy;
+  switch (k) {
+    case 1: launch_lattice<1>(table, Gx, G, idx, N, logdet, st); break;
+    case 2: launch_lattice<2>(table, Gx, G, idx, N, logdet, st); break;
+    case 3: launch_lattice<3>(table, Gx, G, idx, N, logdet, st); break;
+    case 4: launch_lattice<4>(table, Gx, G, idx, N, logdet, st); break;
+    case 5: launch_lattice<5>(table, Gx, G, idx, N, logdet, st); break;
+    case 6: launch_lattice<6>(table, Gx, G, idx, N, logdet, st); break;
+    case 7: launch_lattice<7>(table, Gx, G, idx, N, logdet, st); break;
+    case 8: launch_lattice<8>(table, Gx, G, idx, N, logdet, st); break;
+    case 9: launch_lattice<9>(table, Gx, G, idx, N, logdet, st); break;
+    case 10: launch_lattice<10>(table, Gx, G, idx, N, logdet, st); break;
+    case 11: launch_lattice<11>(table, Gx, G, idx, N, logdet, st); break;
+    default: launch_lattice<12>(table, Gx, G, idx, N, logdet, st); break;
+  }
+  B200BO_CHECK_LAUNCH("dpp_logdet_score_lattice");
+  return 0;
+}
 
 int b200bo_dpp_logdet_score(const double* pool, int pool_size, const int32_t* idx, long long N, int k, double gamma,
                             double* logdet, void* stream) {

@@ -53,6 +53,9 @@ class diverse_data_generator:
         self.combination_sampler = combination_finder()
         self.device = "cuda:0"
         self._X_dev = None
+        self._lat = None
+        self._lat_key = None
+        self._tables = {}
 
     # ------------------------------------------------------------------ bookkeeping (data_gen.py:110-171)
     @property
@@ -140,8 +143,20 @@ class diverse_data_generator:
         return host.iid_comb_locs(combination[0], combination[1], sample_size, self.options["seed"])
 
     def score_sets(self, idx: torch.Tensor, gamma=None) -> torch.Tensor:
-        """log det for index sets idx (N,k) int32 on device -> (N,) f64 on device."""
-        return ops.dpp_logdet_score(self._pool_device(), idx, self.gamma if gamma is None else gamma)
+        """log det for index sets idx (N,k) int32 on device -> (N,) f64 on device. On the constructX lattice the
+        L-ensemble entries come from a per-gamma table (same values bit for bit, csrc/dpp.cu lattice variant)."""
+        gamma = self.gamma if gamma is None else gamma
+        pool = self._pool_device()
+        if self._lat_key is not pool:
+            self._lat = ops.dpp_lattice_of(self.X)
+            self._lat_key = pool
+            self._tables = {}
+        if self._lat is not None and idx.shape[1] <= 12:
+            key = float(gamma)
+            if key not in self._tables:
+                self._tables[key] = ops.dpp_table(self._lat, key, pool.device)
+            return ops.dpp_logdet_score_lattice(self._lat, self._tables[key], idx)
+        return ops.dpp_logdet_score(pool, idx, gamma)
 
     def sub_dpp(self):
         if self.gamma is None and self.training_size == 10:

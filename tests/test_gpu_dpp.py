@@ -139,3 +139,50 @@ def test_full_size_properties(lattice_grid):
     shifted = lattice_grid + np.array([1000.0, -500.0])
     s = _score(shifted, idx[:5000], 1e-5)
     assert np.allclose(s, base[:5000], rtol=1e-6)
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 10, 12])
+def test_lattice_table_variant_is_bit_identical(golden, k):
+    """constructX pools: entries come from a (|dy|,|dx|) table built by the same code — scores must not change at all,
+    on the reference's integer lattice and on the half-step lattice of configs[3]."""
+    from b200bo import ops
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(k)
+    for lat in (ops.Lattice(100, 100), ops.Lattice(200, 200, 0.0, 0.0, 0.5), ops.Lattice(37, 21, 3.0, -2.0, 0.25)):
+        pool = lat.points(dev)
+        assert ops.dpp_lattice_of(pool) is not None
+        idx = torch.as_tensor(np.stack([rng.choice(lat.G, k, replace=False) for _ in range(3000)]).astype(np.int32), device=dev)
+        for gamma in (1e-5, 1e-4, 3e-3):
+            a = ops.dpp_logdet_score(pool, idx, gamma)
+            b = ops.dpp_logdet_score_lattice(lat, ops.dpp_table(lat, gamma, dev), idx)
+            assert torch.equal(a, b) or (torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(a[~torch.isnan(a)], b[~torch.isnan(b)]))
+
+
+def test_lattice_detection_rejects_inexact_pools():
+    from b200bo import ops
+    dev = torch.device("cuda:0")
+    assert ops.dpp_lattice_of(ops.Lattice(10, 10, 0.0, 0.0, 0.1).points(dev)) is None       # 0.1 steps: differences inexact
+    assert ops.dpp_lattice_of(torch.rand(50, 2, dtype=torch.float64, device=dev)) is None
+    idx = torch.tensor([[0, 5, 200]], dtype=torch.int32, device=dev)                          # out-of-range node -> NaN
+    lat = ops.Lattice(10, 10)
+    assert torch.isnan(ops.dpp_logdet_score_lattice(lat, ops.dpp_table(lat, 1e-3, dev), idx)).all()
+
+
+def test_generator_uses_lattice_path_with_same_results(golden):
+    """data_gen.generate() on the reference's pool goes through the table variant; distribution identical to the
+    generic scorer's."""
+    import data_gen
+    from b200bo import ops
+    d = data_gen.diverse_data_generator()
+    d.options["bounds"] = [(0, 100), (0, 100)]
+    d.options["N_samples"] = 2000
+    d.options["seed"] = 3
+    d.gamma = 1e-5
+    d.training_size = 10
+    d.generate()
+    assert d._lat is not None and 1e-5 in d._tables
+    raw = ops.dpp_logdet_score(d._pool_device(), d._pos_sorted, 1e-5)
+    assert torch.equal(raw, d.score_sets(d._pos_sorted))                 # table variant == generic, bit for bit
+    _, z = ops.dpp_zscore(raw)                                           # same mean / sd (order-independent sums aside)
+    assert np.allclose(z.cpu().numpy(), d.data[d.key]["scores"], rtol=1e-12, atol=1e-12)
+    assert np.all(np.diff(d.data[d.key]["scores"]) >= 0)
