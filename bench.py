@@ -517,8 +517,9 @@ def bench_dpp(dev):
     d.generate()
     tt = d.tracker["time-tracking"]
     out["generate_n1e4"] = {"seconds": tt["Total"], "host_rng_and_unrank_share": tt["sampling"], "scoring_share": tt["scoring"],
-                            "note": "element ranks are drawn by CPython/numpy generators exactly as the reference does (parity of "
-                                    "chosen sets); un-ranking, scoring, statistics and the sort run on the GPU"}
+                            "note": "per-element seeds from numpy's legacy generator on the host (as data_gen.py:866-867); the "
+                                    "seeded Mersenne-Twister randint per element (csrc/mt_rank.cu, bit-exact vs CPython), "
+                                    "un-ranking, scoring, statistics and the sort run on the GPU; reference: 3.22 s (SURVEY.md 6)"}
     # CPU: the oracle's twoD_score restatement (numpy slogdet), one core, bounded sample
     from oracle import dpp as odpp
     pool_h = pool.cpu().numpy()

@@ -85,6 +85,15 @@ int b200bo_dpp_zscore(const double* logdet, long long N, double* stats, double* 
 int b200bo_unrank_u128(const uint64_t* binom_lo, const uint64_t* binom_hi, const uint64_t* m_lo, const uint64_t* m_hi,
                        uint64_t total_lo, uint64_t total_hi, int n, int k, long long N, int32_t* out, void* stream);
 
+/* element ranks of the ranked-DPP sampler, drawn as CPython draws them: for every seeds[i] (int64, the values
+ * np.random.randint hands to random.seed) out[i] = the value of  random.seed(seeds[i]); random.randint(0, n - 1)
+ * under CPython 3.9 rules (non-int seed -> (size_t) hash; MT19937 init_by_array; _randbelow by rejection on
+ * getrandbits(n.bit_length())). Replaces the loop at Src/data_gen.py:868-871. n = (n_hi, n_lo) < 2^128, > 0.
+ * out_lo / out_hi (N) uint64; fail (1) int32 is incremented for elements that needed more than 56 rejection
+ * rounds (probability < 2^-56 each; redo those on the host). Bit-exact. */
+int b200bo_mt_seeded_randbelow(const int64_t* seeds, long long N, uint64_t n_lo, uint64_t n_hi, uint64_t* out_lo,
+                               uint64_t* out_hi, int32_t* fail, void* stream);
+
 /* ---- K-E  Wildcat Wells --------------------------------------------------------
  * replaces objectives.wildcatwells (Src/objectives.py:107-218, N = 1 peak, d = 2) and the
  * 10 201 x 3 SimplexNoise.simplexNoise calls inside it (Src/SimpleNoise.py:85-172).

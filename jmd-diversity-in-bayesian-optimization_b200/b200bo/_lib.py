@@ -25,6 +25,7 @@ PROTOTYPES = {
     "b200bo_dpp_stats_workspace_bytes": (c_size_t, [c_longlong]),
     "b200bo_dpp_zscore": (c_int, [P, c_longlong, P, P, P, c_size_t, P]),
     "b200bo_unrank_u128": (c_int, [P, P, P, P, c_uint64, c_uint64, c_int, c_int, c_longlong, P, P]),
+    "b200bo_mt_seeded_randbelow": (c_int, [P, c_longlong, c_uint64, c_uint64, P, P, P, P]),
     "b200bo_wildcat_surface": (c_int, [P, P, P, P, P, P, c_int, P]),
     "b200bo_fp64_fma_probe": (c_longlong, [P, c_int, c_int, P]),
     "b200bo_wildcat_eval": (c_int, [P, P, P, P, c_longlong, P]),

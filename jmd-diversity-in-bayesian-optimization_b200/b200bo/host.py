@@ -94,6 +94,12 @@ def iid_comb_locs(n_pool: int, k: int, n_samples: int, seed):
     return out
 
 
+def iid_comb_seeds(n_samples: int, seed):
+    """The per-element seeds of data_gen.iid_comb_locs' big branch (data_gen.py:866-867): legacy numpy MT19937."""
+    st = np.random.RandomState(seed) if seed is not None else np.random.RandomState()
+    return st.randint(low=np.iinfo(np.int32).min, high=np.iinfo(np.int32).max, size=n_samples).astype(np.int64)
+
+
 def unrank_host(n: int, k: int, m: int):
     """Arbitrary-precision un-ranking for combinations beyond 128 bits (Combination.py:131-170)."""
     if k > n:

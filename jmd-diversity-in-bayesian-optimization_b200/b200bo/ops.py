@@ -164,6 +164,39 @@ def unrank(n: int, k: int, ranks, device) -> torch.Tensor:
     return out
 
 
+def seeded_randint_u128(seeds, n: int, device):
+    """For every int seed: ``random.seed(np.int64(seed)); random.randint(0, n - 1)`` under CPython 3.9 rules, on the
+    device (csrc/mt_rank.cu). seeds: int64 array-like. Returns (lo, hi) int64 tensors holding the uint64 halves."""
+    import numpy as np
+    if not 0 < n < 1 << 128:
+        raise _lib.B200boError("seeded_randint_u128: n must be in (0, 2^128)")
+    sd = torch.as_tensor(np.ascontiguousarray(seeds, dtype=np.int64), device=device)
+    N = sd.numel()
+    lo = torch.empty(N, dtype=torch.int64, device=device)
+    hi = torch.empty(N, dtype=torch.int64, device=device)
+    fail = torch.zeros(1, dtype=torch.int32, device=device)
+    mask = (1 << 64) - 1
+    check(_lib.load().b200bo_mt_seeded_randbelow(_ptr(sd), N, n & mask, n >> 64, _ptr(lo), _ptr(hi), _ptr(fail), _stream()),
+          "mt_seeded_randbelow")
+    if int(fail.item()):
+        raise _lib.B200boError("seeded_randint_u128: rejection sampling did not terminate in 56 rounds")
+    return lo, hi
+
+
+def unrank_u128(n: int, k: int, m_lo: torch.Tensor, m_hi: torch.Tensor) -> torch.Tensor:
+    """Un-rank device-resident 128-bit ranks (uint64 halves stored as int64) -> (N,k) int32 index sets."""
+    lib = _lib.load()
+    device = m_lo.device
+    lo_t, hi_t, total = _binom_table(n, k, device)
+    mask = (1 << 64) - 1
+    N = m_lo.numel()
+    out = torch.empty((N, k), dtype=torch.int32, device=device)
+    if N:
+        check(lib.b200bo_unrank_u128(_ptr(lo_t), _ptr(hi_t), _ptr(m_lo), _ptr(m_hi), total & mask, total >> 64, n, k, N,
+                                     _ptr(out), _stream()), "unrank_u128")
+    return out
+
+
 # ------------------------------------------------------------------ K-E
 
 def wildcat_surface(hseed: torch.Tensor, vecs: torch.Tensor, peak_xy: torch.Tensor, smooth: torch.Tensor,

@@ -167,8 +167,17 @@ class diverse_data_generator:
             raise NotImplementedError("on-disk CSV mode is outside the hot path")
         if self.options["time-debug"]:
             t_setup = time.perf_counter()
-        elements = self.iid_comb_locs()
-        pos = self.combination_sampler.find_elms(self.X.shape[0], self.training_size, elements, device=self.device)
+        import math
+        total = math.comb(self.X.shape[0], self.training_size)
+        if np.iinfo(np.int64).max < total < 1 << 127:
+            # the C(n,k) > int64 branch of iid_comb_locs (data_gen.py:865-871) entirely on the device: per-element
+            # seeded Mersenne Twister + randint (csrc/mt_rank.cu), then the 128-bit un-ranker — same ranks bit for bit
+            seeds = host.iid_comb_seeds(self.options["N_samples"], self.options["seed"])
+            m_lo, m_hi = ops.seeded_randint_u128(seeds, total + 1, self.device)
+            pos = ops.unrank_u128(self.X.shape[0], self.training_size, m_lo, m_hi)
+        else:
+            elements = self.iid_comb_locs()
+            pos = self.combination_sampler.find_elms(self.X.shape[0], self.training_size, elements, device=self.device)
         if bool((pos < 0).any()):
             raise Exception("check previous")            # rank == C(n,k): the reference raises (Combination.py:150-153)
         if self.options["time-debug"]:

@@ -186,3 +186,42 @@ def test_generator_uses_lattice_path_with_same_results(golden):
     _, z = ops.dpp_zscore(raw)                                           # same mean / sd (order-independent sums aside)
     assert np.allclose(z.cpu().numpy(), d.data[d.key]["scores"], rtol=1e-12, atol=1e-12)
     assert np.all(np.diff(d.data[d.key]["scores"]) >= 0)
+
+
+def test_device_seeded_randint_equals_cpython():
+    """csrc/mt_rank.cu vs CPython's own generator: random.seed(s); random.randint(0, n - 1) with the 3.9 rule for
+    numpy-integer seeds (oracle/refshim.py:py39_seed) — bit-exact for every seed class and several range widths."""
+    import math
+    import random
+    from b200bo import ops
+    from oracle import refshim
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(0)
+    seeds = np.concatenate([np.array([0, 1, -1, -2, 2 ** 31 - 2, -2 ** 31, 12345, -12345], dtype=np.int64),
+                            rng.integers(-2 ** 31, 2 ** 31 - 1, size=3000)])
+    for n in (math.comb(10000, 10) + 1, 5, 2 ** 32, 2 ** 32 + 1, 2 ** 64, 2 ** 100 + 12345, 2 ** 127 - 1, 1):
+        lo, hi = ops.seeded_randint_u128(seeds, n, dev)
+        got = [(int(h) & (2 ** 64 - 1)) << 64 | (int(l) & (2 ** 64 - 1)) for l, h in zip(lo.cpu().numpy(), hi.cpu().numpy())]
+        rnd = random.Random()
+        for s, g in zip(seeds, got):
+            rnd.seed(refshim.seed_to_py39_int(np.int64(s)))
+            assert g == rnd.randint(0, n - 1), (int(s), n)
+
+
+def test_generate_draws_the_reference_ranks_on_device(golden):
+    """generate() on the 10 000-node pool: device-drawn ranks + device un-ranking give the sets the reference drew."""
+    import data_gen
+    g = golden("dpp.npz")
+    d = data_gen.diverse_data_generator()
+    d.options["bounds"] = [(0, 100), (0, 100)]
+    d.options["N_samples"] = 10000
+    d.options["seed"] = 0
+    d.gamma = float(g["gen_s0_gamma"][0])
+    d.training_size = 10
+    d.generate()
+    host_ranks = d.iid_comb_locs()                       # the host path (Python big ints), same stream
+    from b200bo import ops
+    pos_host = ops.unrank(10000, 10, host_ranks, torch.device("cuda:0")).cpu().numpy()
+    assert np.array_equal(np.sort(d._pos_sorted.cpu().numpy().reshape(-1, 10), axis=0)[:0], pos_host[:0])   # shapes
+    assert set(map(tuple, d._pos_sorted.cpu().numpy())) == set(map(tuple, pos_host))
+    assert set(map(tuple, pos_host)) == set(map(tuple, g["gen_s0_pos"]))
