@@ -285,8 +285,19 @@ def run_b200(args):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "fp64", "kernel": "grid_acq_lattice_kernel<NI> (K-B)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+    hbm_peak_gbs = None
+    try:
+        hbm_peak_gbs = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+    except Exception:
+        pass
+    kb_avg_ms = kb_ms / max(1, len(kb))
+    roofline = {"bound": "tensor", "bound_detail": "FP64 tensor pipe: mma.sync.m8n8k4.f64 (DMMA), which shares the SM's FP64 "
+                                                   "pipe with DFMA (profiles/fp64_peaks_r1.json); not HBM (see hbm_view)",
+                "kernel": "grid_acq_lattice_kernel<NI> (K-B)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak if peak else None, "traffic": traffic,
+                "hbm_view": {"algorithmic_bytes_per_launch_mean": float(np.mean([T * (8 * ops.wfrag_doubles(n) + 24 * n + 56) for n, _ in kb])) if kb else None,
+                             "achieved_gbs": (float(np.mean([T * (8 * ops.wfrag_doubles(n) + 24 * n + 56) for n, _ in kb])) / (kb_avg_ms * 1e-3) / 1e9) if kb else None,
+                             "peak_gbs_of_measured": hbm_peak_gbs},
                 "peak_probe_this_run": peak_probe, "peak_microbench_file": peak_file,
                 "peak_source": "max(FP64 FMA issue rate measured in this run by b200bo_fp64_fma_probe, DFMA/DMMA rate of "
                                "tools/microbench/fp64_peaks.cu committed in profiles/fp64_peaks_r1.json); DMMA and DFMA share "
