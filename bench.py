@@ -422,13 +422,47 @@ def bench_other_configs(dev, surf, S):
     run("configs[2]_fit_every_iteration_tol_disabled", ops.Lattice(100, 100), 1000, 100, None, -1.0)
     run("configs[2]_fit_every_iteration_tol_0.1", ops.Lattice(100, 100), 1000, 100, None, 0.1)
     run("configs[3]_grid200_fixed_theta_slice", ops.Lattice(200, 200, 0.0, 0.0, 0.5), 1184, 100, theta, -1.0)
+    # configs[0]: ONE BO run through the reference-facing API (optimizer.optimize -> BOloop_fixparam), 10 initial
+    # points, fixed theta, EI over the 100 x 100 lattice, 50 iterations — latency of a single trial, wall clock
+    import objectives as objmod
+    from Optimizers import optimizer
+    synth = objmod.objectives()
+    synth.device = str(dev)
+    synth.bounds = [(0, 100), (0, 100)]
+    synth.seed = 0
+    synth.args = {"N": 1, "Smoothness": 0.2, "rug_freq": 1, "rug_amp": 0.2}
+    t0 = time.perf_counter()
+    f = synth.generate_cont()
+    t_surface = time.perf_counter() - t0
+    opt = optimizer()
+    opt.max_iter = 50
+    opt.opt = "BO-fixparam"
+    opt.options["tol"] = -1.0
+    opt.options["device"] = str(dev)
+    opt.bounds = synth.bounds
+    names = ("likelihood.noise_covar.raw_noise", "mean_module.constant", "covar_module.raw_outputscale",
+             "covar_module.base_kernel.raw_lengthscale")
+    opt.paramset = {k: [v] for k, v in zip(names, AUTHOR_RAW)}
+    pick = np.random.default_rng(0).choice(10000, 10, replace=False)
+    opt.train = np.stack([pick % 100, pick // 100], axis=1).astype(np.float64)
+    opt.optimize(f)                                                # warm-up
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        r1 = opt.optimize(f)
+    torch.cuda.synchronize(dev)
+    t_run = (time.perf_counter() - t0) / 3
+    out["configs[0]_single_run_through_optimizer_api"] = {"iterations": int(r1.nit), "seconds_per_run": t_run,
+                                                           "bo_iterations_per_s": int(r1.nit) / t_run,
+                                                           "wildcat_surface_and_interpolant_seconds": t_surface,
+                                                           "note": "wall clock incl. Python, objective table, result packing; "
+                                                                   "one trial cannot fill the GPU - latency figure"}
     # bootstrap of a (1000 trials x 102) gap-curve matrix, 1000 replicates; the oracle restatement timed on a slice
     import random
     import utils
     from oracle import bootstrap as ob
     data = np.maximum.accumulate(rng.uniform(0, 100, size=(1000, 102)), axis=1)[:, ::-1].copy()
-    random.seed(0)
-    idx = torch.as_tensor(ob.draw_indices(1000, 1000), device=dev)
+    idx = torch.as_tensor(rng.integers(0, 1000, size=(1000, 1000)).astype(np.int32), device=dev)
     dd = torch.as_tensor(data, device=dev)
     for _ in range(2):
         ops.bootstrap_ci(dd, idx)

@@ -59,7 +59,8 @@ long long b200bo_fp64_fma_probe(double* out, int blocks, int iters, void* stream
  * replaces diverse_data_generator.twoD_score looped over the superset,
  * Src/data_gen.py:484-497 called from :403.
  * pool (P,2) f64; idx (N,k) int32 rows index pool; logdet (N) f64 out.
- * logdet[i] = log det exp(-gamma * D), D_ab = (sqrt(|x_a-x_b|^2))^2; NaN if not PD. */
+ * logdet[i] = log |det exp(-gamma * D)|, D_ab = (sqrt(|x_a-x_b|^2))^2, from the pivots of an LDL^T elimination:
+ * finite on nearly singular S like numpy's slogdet (which the reference calls), -inf when a pivot is exactly 0. */
 int b200bo_dpp_logdet_score(const double* pool, int pool_size, const int32_t* idx, long long N, int k,
                             double gamma, double* logdet, void* stream);
 

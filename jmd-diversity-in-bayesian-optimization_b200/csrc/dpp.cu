@@ -23,6 +23,31 @@ __device__ __forceinline__ double dpp_entry(double ax, double ay, double bx, dou
   return exp(neg_gamma * (d * d));
 }
 
+// log |det| of the packed symmetric matrix by an LDL^T elimination in natural order: sum_j log |d_j|.
+// The reference takes np.linalg.slogdet(S)[1] (data_gen.py:497), i.e. log|det| from an LU factorisation, which stays
+// finite (and informative: the leading pivots dominate) on the nearly singular S of very small gamma where a Cholesky
+// would stop at the first non-positive pivot — gammacalc (data_gen.py:758-842) ranks exactly those cases. For a
+// positive definite S the pivots are the Cholesky pivots L_jj^2. A zero pivot gives -inf, as slogdet does.
+template <int K>
+__device__ __forceinline__ double ldl_logabsdet(double (&A)[K * (K + 1) / 2]) {
+  double acc = 0.0;
+  bool singular = false;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const double d = A[j * (j + 1) / 2 + j];
+    singular = singular || d == 0.0;
+    acc += log(fabs(d));
+    const double inv = 1.0 / d;
+#pragma unroll
+    for (int c = j + 1; c < K; ++c) {
+      const double lc = A[c * (c + 1) / 2 + j] * inv;      // L_cj
+#pragma unroll
+      for (int r = c; r < K; ++r) A[r * (r + 1) / 2 + c] = fma(-A[r * (r + 1) / 2 + j], lc, A[r * (r + 1) / 2 + c]);
+    }
+  }
+  return singular ? -INFINITY : acc;
+}
+
 template <int K>
 __global__ void __launch_bounds__(128)
 dpp_logdet_reg_kernel(const double2* __restrict__ pool, const int32_t* __restrict__ idx, long long N, double neg_gamma,
@@ -45,24 +70,7 @@ dpp_logdet_reg_kernel(const double2* __restrict__ pool, const int32_t* __restric
     for (int c = 0; c < r; ++c) A[r * (r + 1) / 2 + c] = dpp_entry(px[r], py[r], px[c], py[c], neg_gamma);
     A[r * (r + 1) / 2 + r] = 1.0;   // exp(-gamma * 0)
   }
-  double acc = 0.0;
-  bool ok = true;
-#pragma unroll
-  for (int j = 0; j < K; ++j) {
-    double d = A[j * (j + 1) / 2 + j];
-    ok = ok && (d > 0.0);
-    acc += log(d);
-    double inv = 1.0 / sqrt(d);
-#pragma unroll
-    for (int r = j + 1; r < K; ++r) A[r * (r + 1) / 2 + j] *= inv;
-#pragma unroll
-    for (int c = j + 1; c < K; ++c) {
-      double lcj = A[c * (c + 1) / 2 + j];
-#pragma unroll
-      for (int r = c; r < K; ++r) A[r * (r + 1) / 2 + c] = fma(-A[r * (r + 1) / 2 + j], lcj, A[r * (r + 1) / 2 + c]);
-    }
-  }
-  out[i] = ok ? acc : nan("");
+  out[i] = ldl_logabsdet<K>(A);
 }
 
 // ---- lattice variant ------------------------------------------------------------------------------------
@@ -102,22 +110,7 @@ dpp_logdet_lattice_kernel(const double* __restrict__ table, int Gx, int G, const
     for (int c = 0; c < r; ++c) A[r * (r + 1) / 2 + c] = __ldg(&table[abs(iy[r] - iy[c]) * Gx + abs(ix[r] - ix[c])]);
     A[r * (r + 1) / 2 + r] = 1.0;
   }
-  double acc = 0.0;
-#pragma unroll
-  for (int j = 0; j < K; ++j) {
-    double d = A[j * (j + 1) / 2 + j];
-    ok = ok && (d > 0.0);
-    acc += log(d);
-    double inv = 1.0 / sqrt(d);
-#pragma unroll
-    for (int r = j + 1; r < K; ++r) A[r * (r + 1) / 2 + j] *= inv;
-#pragma unroll
-    for (int c = j + 1; c < K; ++c) {
-      double lcj = A[c * (c + 1) / 2 + j];
-#pragma unroll
-      for (int r = c; r < K; ++r) A[r * (r + 1) / 2 + c] = fma(-A[r * (r + 1) / 2 + j], lcj, A[r * (r + 1) / 2 + c]);
-    }
-  }
+  const double acc = ldl_logabsdet<K>(A);
   out[i] = ok ? acc : nan("");
 }
 
@@ -137,7 +130,7 @@ dpp_logdet_smem_kernel(const double2* __restrict__ pool, const int32_t* __restri
   double* px = sm + (size_t)k * k;
   double* py = px + k;
   __shared__ double s_acc;
-  __shared__ int s_ok;
+  __shared__ int s_sing;
   for (long long set = blockIdx.x; set < N; set += gridDim.x) {
     const int32_t* row = idx + set * k;
     for (int a = threadIdx.x; a < k; a += blockDim.x) {
@@ -145,7 +138,7 @@ dpp_logdet_smem_kernel(const double2* __restrict__ pool, const int32_t* __restri
       px[a] = p.x;
       py[a] = p.y;
     }
-    if (threadIdx.x == 0) { s_acc = 0.0; s_ok = 1; }
+    if (threadIdx.x == 0) { s_acc = 0.0; s_sing = 0; }
     __syncthreads();
     for (int e = threadIdx.x; e < k * k; e += blockDim.x) {
       int r = e / k, c = e - r * k;
@@ -155,25 +148,23 @@ dpp_logdet_smem_kernel(const double2* __restrict__ pool, const int32_t* __restri
     for (int j = 0; j < k; ++j) {
       double d = A[j * k + j];
       __syncthreads();   // everyone has read the pivot before column j is scaled
-      if (threadIdx.x == 0) {
-        if (!(d > 0.0)) s_ok = 0;
-        s_acc += log(d);
+      if (threadIdx.x == 0) {                                // log|det| as slogdet: see ldl_logabsdet
+        s_acc += log(fabs(d));
+        if (d == 0.0) s_sing = 1;
       }
-      double inv = 1.0 / sqrt(d);
-      for (int r = j + 1 + threadIdx.x; r < k; r += blockDim.x) A[r * k + j] *= inv;
-      __syncthreads();
-      // trailing update of the lower triangle: rows r > j, cols j < c <= r
+      const double inv = 1.0 / d;
+      // trailing update of the lower triangle: rows r > j, cols j < c <= r  (A_rc -= A_rj * (A_cj / d))
       int m = k - j - 1;
       for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
         int rr = e / m, cc = e - rr * m;
         if (cc <= rr) {
           int r = j + 1 + rr, c = j + 1 + cc;
-          A[r * k + c] = fma(-A[r * k + j], A[c * k + j], A[r * k + c]);
+          A[r * k + c] = fma(-A[r * k + j], A[c * k + j] * inv, A[r * k + c]);
         }
       }
       __syncthreads();
     }
-    if (threadIdx.x == 0) out[set] = s_ok ? s_acc : nan("");
+    if (threadIdx.x == 0) out[set] = s_sing ? -INFINITY : s_acc;
     __syncthreads();
   }
 }
