@@ -457,6 +457,27 @@ def bench_other_configs(dev, surf, S):
                                                            "wildcat_surface_and_interpolant_seconds": t_surface,
                                                            "note": "wall clock incl. Python, objective table, result packing; "
                                                                    "one trial cannot fill the GPU - latency figure"}
+    # the same single trial at engine level: eager launches vs the whole run replayed as one CUDA graph
+    lat1 = ops.Lattice(100, 100)
+    pts1 = lat1.points(dev)
+    obj1 = surf[:1, :100, :100].reshape(1, -1).contiguous()
+    X1 = pts1[torch.as_tensor(pick, device=dev)].unsqueeze(0)
+    y1 = obj1[0][torch.as_tensor(pick, device=dev)].double().unsqueeze(0)
+    bo1 = engine.BatchedBO(pts1, obj1, torch.zeros(1, dtype=torch.int32, device=dev), X1, y1, 50, theta=theta, tol=-1.0,
+                           lattice=lat1, check_every=0)
+    lat_ms = {}
+    for mode in ("eager", "graph"):
+        runner = bo1.run if mode == "eager" else bo1.run_graphed
+        for _ in range(2):
+            bo1.reset(X1, y1); runner()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            bo1.reset(X1, y1); runner()
+        torch.cuda.synchronize(dev)
+        lat_ms[mode] = (time.perf_counter() - t0) / 10 * 1e3
+    out["configs[0]_single_trial_engine_latency_ms"] = {"eager": lat_ms["eager"], "cuda_graph_replay": lat_ms["graph"],
+                                                        "iterations": 50, "note": "BatchedBO.run vs run_graphed, wall clock per run"}
     # bootstrap of a (1000 trials x 102) gap-curve matrix, 1000 replicates; the oracle restatement timed on a slice
     import random
     import utils

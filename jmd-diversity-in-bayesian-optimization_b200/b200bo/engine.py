@@ -223,6 +223,27 @@ class BatchedBO:
                       self.picked, self.nit, self.max_iter, it, self.tol, self.optimal_y)
         self.launches += 1
 
+    def run_graphed(self) -> BOResult:
+        """The whole run as ONE CUDA graph: the first call runs eagerly (warm-up: lazy module loads, attribute
+        settings) and captures the launch sequence of every iteration (no host synchronisation exists inside when
+        check_every == 0); later calls — after ``reset()`` with new initial sets of the same shape — replay it with
+        one host call instead of ~6 launches per iteration. Latency lever for small batches (a single trial is
+        launch-bound); identical results (same kernels, same order)."""
+        if self.check_every or self.theta_rest is not None:
+            raise ops._lib.B200boError("run_graphed needs check_every=0 and no theta_rest (host logic inside the loop)")
+        if getattr(self, "_graph", None) is None:
+            X0, y0 = self.X[:, :self.n0].clone(), self.y[:, :self.n0].clone()
+            self.run()                                         # eager warm-up on the current stream
+            torch.cuda.synchronize()
+            self.reset(X0, y0)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._graph_result = self.run()
+            self._graph = g
+        self._graph.replay()
+        return self._graph_result
+
     def run(self) -> BOResult:
         ops.bo_init(self.y, self.n, self.best_f, self.yall, self.picked, self.nit, self.max_iter, self.tol, self.optimal_y)
         self.launches += 1

@@ -139,3 +139,34 @@ def test_incremental_equals_full_recompute_on_a_larger_batch(golden, lattice_gri
     var = bo.theta[:, 2:3] - bo.ss_s
     assert torch.allclose(mu, dbg["mu"], rtol=1e-9, atol=1e-9 * float(dbg["mu"].abs().max()))
     assert torch.allclose(var, dbg["var"], rtol=1e-8, atol=1e-10 * float(bo.theta[0, 2]))
+
+
+@pytest.mark.parametrize("fit_mode", [False, True])
+def test_cuda_graph_replay_equals_eager_run(golden, lattice_grid, fit_mode):
+    """BatchedBO.run_graphed(): the captured launch sequence replayed on new initial sets gives what the eager loop
+    gives (fixed theta with rank-1 appends, and fit-before-every-acquisition)."""
+    from b200bo import engine, fit, ops
+    dev = torch.device("cuda:0")
+    surf = golden("wildcat.npz")["surf_2"][:100, :100].reshape(1, -1).astype(np.float32)
+    rng = np.random.default_rng(11)
+    T, n0, iters = 6, 10, 12
+    grid = torch.as_tensor(lattice_grid, device=dev)
+    obj = torch.as_tensor(surf, device=dev)
+    sid = torch.zeros(T, dtype=torch.int32, device=dev)
+    theta = None if fit_mode else torch.as_tensor(ogp.raw_to_theta(AUTHOR_THETA_RAW), device=dev)
+
+    def sets():
+        idx = np.stack([rng.choice(10000, n0, replace=False) for _ in range(T)])
+        return torch.as_tensor(lattice_grid[idx], device=dev), torch.as_tensor(surf[0][idx].astype(np.float64), device=dev)
+
+    X0, y0 = sets()
+    mk = lambda: engine.BatchedBO(grid, obj, sid, X0, y0, iters, theta=theta, tol=-1.0, check_every=0,
+                                  fitter=fit.LBFGSFitter(T, dev) if fit_mode else None)
+    bo_g, bo_e = mk(), mk()
+    for _ in range(3):                                   # first call captures, the next two replay on fresh inputs
+        bo_g.reset(X0, y0); bo_e.reset(X0, y0)
+        rg = bo_g.run_graphed()
+        re_ = bo_e.run()
+        torch.cuda.synchronize()
+        assert torch.equal(rg.picked, re_.picked) and torch.equal(rg.yall, re_.yall) and torch.equal(rg.nit, re_.nit)
+        X0, y0 = sets()
