@@ -10,7 +10,7 @@ import os
 from ctypes import c_char_p, c_double, c_int, c_int32, c_longlong, c_size_t, c_uint64, c_void_p
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG_DIR, "lib", "libb200bo.so")
+LIB_PATH = os.environ.get("B200BO_LIB_PATH") or os.path.join(PKG_DIR, "lib", "libb200bo.so")   # override: kernel A/B experiments
 
 P = c_void_p   # every device / host pointer crosses the ABI as void*
 

@@ -22,6 +22,14 @@
 #include <limits.h>
 #include <stdlib.h>
 
+// tuning switches of the lattice kernel (A/B-tested on the GPU; defaults = what measured best)
+#ifndef KB_MINB_SMALL
+#define KB_MINB_SMALL 5      // resident 128-thread CTAs per SM the register allocator targets while NI <= 8
+#endif
+#ifndef KB_MU2
+#define KB_MU2 0             // 1: two interleaved accumulators for the posterior-mean dot product
+#endif
+
 namespace b200bo {
 
 constexpr int GA_THREADS = 128;
@@ -348,6 +356,7 @@ __device__ __forceinline__ void lattice_tile(const double* __restrict__ wsm, con
   int ix0 = index_of(0), ix1 = index_of(1);
   double kv0 = __ldg(tab + ix0), kv1 = __ldg(tab + ix1);
   mu_part = 0.0;
+  double mu_odd = 0.0;
   masked = 0;
 #pragma unroll
   for (int J = 0; J < NJ; ++J) {
@@ -361,13 +370,15 @@ __device__ __forceinline__ void lattice_tile(const double* __restrict__ wsm, con
     }
     // padded observations (j >= n) meet zero columns of L^-1 and alpha = 0: any finite value is harmless
     masked |= (ix == 0 && 4 * J + jrow < n) ? 1 : 0;       // dxi < Gx, so index 0 <=> the observed point itself
-    mu_part = fma(kv, al[4 * J + jrow], mu_part);
+    if (KB_MU2 && (J & 1)) mu_odd = fma(kv, al[4 * J + jrow], mu_odd);
+    else mu_part = fma(kv, al[4 * J + jrow], mu_part);
 #pragma unroll
     for (int I = J / 2; I < NI; ++I) {
       if (EXACT || I < nI)
         dmma_m8n8k4(acc[I][0], acc[I][1], wsm[(size_t)(I * (I + 1) + J) * 32 + lane], kv);
     }
   }
+  if (KB_MU2) mu_part += mu_odd;
   ss0 = 0.0;
   ss1 = 0.0;
 #pragma unroll
@@ -378,7 +389,7 @@ __device__ __forceinline__ void lattice_tile(const double* __restrict__ wsm, con
 }
 
 template <int NI, int THREADS>
-__global__ void __launch_bounds__(THREADS, (THREADS == 128 ? (NI <= 8 ? 5 : 4) : (THREADS == 256 ? 2 : 1)))
+__global__ void __launch_bounds__(THREADS, (THREADS == 128 ? (NI <= 8 ? KB_MINB_SMALL : 4) : (THREADS == 256 ? 2 : 1)))
 grid_acq_lattice_kernel(const GridAcqParams p) {
   constexpr int NWARPS = THREADS / 32;
   extern __shared__ double sm[];
