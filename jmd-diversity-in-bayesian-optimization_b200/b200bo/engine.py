@@ -162,7 +162,8 @@ class BatchedBO:
         if self.theta_rest is not None and it == 1:
             self._switch_theta(self.theta_rest)
         if not self.fixed:
-            self.fitter.fit_into(self.X, self.y, self.n, self.kernel_id, self.theta, self.status, n_hint)
+            self._timed("fit", n_hint, lambda: self.fitter.fit_into(self.X, self.y, self.n, self.kernel_id, self.theta,
+                                                                    self.status, n_hint))
             self.thetas[:, it] = self.theta
             self.launches += self.fitter.last_launches
         self._timed("gp_chol", n_hint, lambda: self._factorise(it, n_hint))
