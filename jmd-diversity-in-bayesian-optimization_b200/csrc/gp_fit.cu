@@ -82,11 +82,19 @@ struct FitSmem {
 
 // keep exp(-a) per entry between the assembly and the gradient traces where it does not cost occupancy
 template <int NB, int OW>
-__host__ __device__ constexpr bool fit_ecache() { return OW == 8 ? NB <= 6 : (NB == 7 || NB == 8); }
+__host__ __device__ constexpr bool fit_ecache() { return OW == 8 ? NB <= 6 : NB == 8; }
+
+// the staging buffer is walked in NCH chunks: two for the 16 x 16 grid at NB = 7 (n = 96 ... 111, the costliest fits of
+// a 100-iteration run), which brings the CTA to 90 KB of shared memory so that two of them share an SM
+template <int NB, int OW>
+__host__ __device__ constexpr int fit_kchunks() { return (OW == 16 && NB == 7) ? 2 : 1; }
+template <int NB, int OW>
+__host__ __device__ constexpr int fit_kchunk_slots() { return (NB * (NB + 1) / 2 + fit_kchunks<NB, OW>() - 1) / fit_kchunks<NB, OW>(); }
 
 template <int NB, int OW>
 __host__ __device__ constexpr size_t fit_smem_doubles() {
-  return (size_t)(NB * (NB + 1) / 2) * (OW * OW) * (fit_ecache<NB, OW>() ? 3 : 2) + 2 * (OW * NB + 2) + 5 * (OW * NB);
+  return (size_t)(NB * (NB + 1) / 2 * (fit_ecache<NB, OW>() ? 2 : 1) + fit_kchunk_slots<NB, OW>()) * (OW * OW) +
+         2 * (OW * NB + 2) + 5 * (OW * NB);
 }
 
 template <int NB, int OW>
@@ -95,7 +103,7 @@ __device__ __forceinline__ FitSmem fit_carve(double* sm) {
   FitSmem s;
   s.dist = sm;
   s.kbuf = s.dist + (size_t)NS * FT;
-  s.ebuf = s.kbuf + (size_t)NS * FT;
+  s.ebuf = s.kbuf + (size_t)fit_kchunk_slots<NB, OW>() * FT;
   s.vbuf = s.ebuf + (fit_ecache<NB, OW>() ? (size_t)NS * FT : 0);
   s.alpha = s.vbuf + 2 * (NP + 2);
   s.dpiv = s.alpha + NP;
@@ -161,35 +169,41 @@ __device__ __forceinline__ void mll_eval_sweep(const FitSmem& s, int n, int kern
     __syncthreads();                       // previous users of vbuf / alpha are done
     // ---- assemble the owned entries: Khat (lower), augmented row NP-1 = y - c
     {
+      constexpr int NCH = fit_kchunks<NB, OW>(), CH = fit_kchunk_slots<NB, OW>();
       int a = 0, b = 0;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int lo = ch * CH, hi = (ch + 1) * CH < NS ? (ch + 1) * CH : NS;
 #pragma unroll 1
-      for (int sl = 0; sl < NS; ++sl) {       // runtime loop: one copy of the exp code
-        const int r = tr + OW * a, c = tc + OW * b;
-        double v = 0.0;
-        if (r < n && c <= r) {
-          if (fit_ecache<NB, OW>()) {
-            if (attempt == 0) {
-              const double a = kern_arg(kernel_id, s.dist[(size_t)sl * FT + tid], ell, a_scale);
-              const double e = exp(-a);
-              s.ebuf[(size_t)sl * FT + tid] = e;
-              v = kern_from_exp(kernel_id, a, e, sc);
+        for (int sl = lo; sl < hi; ++sl) {     // runtime loop: one copy of the exp code
+          const int r = tr + OW * a, c = tc + OW * b;
+          double v = 0.0;
+          if (r < n && c <= r) {
+            if (fit_ecache<NB, OW>()) {
+              const double ka = kern_arg(kernel_id, s.dist[(size_t)sl * FT + tid], ell, a_scale);
+              double e;
+              if (attempt == 0) {
+                e = exp(-ka);
+                s.ebuf[(size_t)sl * FT + tid] = e;
+              } else {
+                e = s.ebuf[(size_t)sl * FT + tid];
+              }
+              v = kern_from_exp(kernel_id, ka, e, sc);
             } else {
-              const double a = kern_arg(kernel_id, s.dist[(size_t)sl * FT + tid], ell, a_scale);
-              v = kern_from_exp(kernel_id, a, s.ebuf[(size_t)sl * FT + tid], sc);
+              v = kern_only(kernel_id, s.dist[(size_t)sl * FT + tid], sc, ell, a_scale);
             }
-          } else {
-            v = kern_only(kernel_id, s.dist[(size_t)sl * FT + tid], sc, ell, a_scale);
+            if (r == c) v += noise + jitter;
+          } else if (r == NP - 1 && c < n) {
+            v = s.yv[c] - cst;
           }
-          if (r == c) v += noise + jitter;
-        } else if (r == NP - 1 && c < n) {
-          v = s.yv[c] - cst;
+          s.kbuf[(size_t)(sl - lo) * FT + tid] = v;
+          if (++b > a) { b = 0; ++a; }
         }
-        s.kbuf[(size_t)sl * FT + tid] = v;
-        if (++b > a) { b = 0; ++a; }
+#pragma unroll
+        for (int sl = 0; sl < NS; ++sl)          // own writes: no barrier needed
+          if (sl >= lo && sl < hi) A[sl] = s.kbuf[(size_t)(sl - lo) * FT + tid];
       }
     }
-#pragma unroll
-    for (int sl = 0; sl < NS; ++sl) A[sl] = s.kbuf[(size_t)sl * FT + tid];     // own writes: no barrier needed
     // ---- sweep pivots 0..n-1
     ok = true;
     int buf = 0;
@@ -268,37 +282,43 @@ __device__ __forceinline__ void mll_eval_sweep(const FitSmem& s, int n, int kern
   for (int a = 0; a < NB; ++a) ar[a] = s.alpha[tr + OW * a];
 #pragma unroll
   for (int b = 0; b < NB; ++b) ac[b] = s.alpha[tc + OW * b];
-#pragma unroll
-  for (int a = 0; a < NB; ++a)
-#pragma unroll
-    for (int b = 0; b <= a; ++b) {
-      const int r = tr + OW * a, c = tc + OW * b;
-      double wa = 0.0;
-      if (r < n && c <= r) {
-        const double a_rc = fma(ar[a], ac[b], A[slot_of(a, b)]);
-        if (c == r) q2 += a_rc;
-        wa = (c == r) ? a_rc : 2.0 * a_rc;            // symmetric: (r,c) and (c,r)
-      }
-      s.kbuf[(size_t)slot_of(a, b) * FT + tid] = wa;
-    }
   {
-    int a = 0, b = 0;
-#pragma unroll 1
-    for (int sl = 0; sl < NS; ++sl) {         // runtime loop: one copy of the exp code
-      const int r = tr + OW * a, c = tc + OW * b;
-      if (r < n && c <= r) {
-        double kl, dk;
-        if (fit_ecache<NB, OW>()) {
-          const double a = kern_arg(kernel_id, s.dist[(size_t)sl * FT + tid], ell, a_scale);
-          kern_pair_from_exp(kernel_id, a, s.ebuf[(size_t)sl * FT + tid], kl, dk);
-        } else {
-          kern_pair(kernel_id, s.dist[(size_t)sl * FT + tid], ell, a_scale, kl, dk);
+    constexpr int NCH = fit_kchunks<NB, OW>(), CH = fit_kchunk_slots<NB, OW>();
+    int ra = 0, rb = 0;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int lo = ch * CH, hi = (ch + 1) * CH < NS ? (ch + 1) * CH : NS;
+#pragma unroll
+      for (int a = 0; a < NB; ++a)
+#pragma unroll
+        for (int b = 0; b <= a; ++b) {
+          if (slot_of(a, b) < lo || slot_of(a, b) >= hi) continue;
+          const int r = tr + OW * a, c = tc + OW * b;
+          double wa = 0.0;
+          if (r < n && c <= r) {
+            const double a_rc = fma(ar[a], ac[b], A[slot_of(a, b)]);
+            if (c == r) q2 += a_rc;
+            wa = (c == r) ? a_rc : 2.0 * a_rc;            // symmetric: (r,c) and (c,r)
+          }
+          s.kbuf[(size_t)(slot_of(a, b) - lo) * FT + tid] = wa;
         }
-        const double wa = s.kbuf[(size_t)sl * FT + tid];
-        q3 = fma(wa, kl, q3);
-        q4 = fma(wa, dk, q4);
+#pragma unroll 1
+      for (int sl = lo; sl < hi; ++sl) {         // runtime loop: one copy of the exp code
+        const int r = tr + OW * ra, c = tc + OW * rb;
+        if (r < n && c <= r) {
+          double kl, dk;
+          if (fit_ecache<NB, OW>()) {
+            const double ka = kern_arg(kernel_id, s.dist[(size_t)sl * FT + tid], ell, a_scale);
+            kern_pair_from_exp(kernel_id, ka, s.ebuf[(size_t)sl * FT + tid], kl, dk);
+          } else {
+            kern_pair(kernel_id, s.dist[(size_t)sl * FT + tid], ell, a_scale, kl, dk);
+          }
+          const double wa = s.kbuf[(size_t)(sl - lo) * FT + tid];
+          q3 = fma(wa, kl, q3);
+          q4 = fma(wa, dk, q4);
+        }
+        if (++rb > ra) { rb = 0; ++ra; }
       }
-      if (++b > a) { b = 0; ++a; }
     }
   }
   double q[5] = {q1, q2, q3, q4, q5};
@@ -350,7 +370,7 @@ __device__ __forceinline__ void fit_load_trial(const FitSmem& s, const double* _
 
 // ---- K-C: one evaluation per trial ------------------------------------------------------------------------
 template <int NB, int OW>
-__global__ void __launch_bounds__(OW * OW, (OW == 8 ? 1 : (NB <= 6 ? 2 : 1)))
+__global__ void __launch_bounds__(OW * OW, (OW == 8 ? 1 : (NB <= 7 ? 2 : 1)))
 mll_sweep_kernel(const double* __restrict__ X, const double* __restrict__ y, const int32_t* __restrict__ n_arr,
                  const double* __restrict__ raw, double* __restrict__ value, double* __restrict__ grad,
                  int32_t* __restrict__ status, int n_max, int kernel_id) {
@@ -383,7 +403,7 @@ mll_sweep_kernel(const double* __restrict__ X, const double* __restrict__ y, con
 // and its gradient, lets thread 0 advance the L-BFGS state machine (lbfgs.cuh) and repeats until the trial
 // converges: one launch per fit, and nobody waits for the slowest trial of the batch between evaluations.
 template <int NB, int OW>
-__global__ void __launch_bounds__(OW * OW, (OW == 8 ? 1 : (NB <= 6 ? 2 : 1)))
+__global__ void __launch_bounds__(OW * OW, (OW == 8 ? 1 : (NB <= 7 ? 2 : 1)))
 gp_fit_sweep_kernel(const double* __restrict__ X, const double* __restrict__ y, const int32_t* __restrict__ n_arr,
                     const double* __restrict__ raw0, int raw0_per_trial, double* __restrict__ theta_out,
                     double* __restrict__ raw_out, double* __restrict__ mll_out, int32_t* __restrict__ iters_out,
