@@ -84,10 +84,10 @@ struct FitSmem {
 template <int NB, int OW>
 __host__ __device__ constexpr bool fit_ecache() { return OW == 8 ? NB <= 6 : NB == 8; }
 
-// the staging buffer is walked in NCH chunks: two for the 16 x 16 grid at NB = 7 (n = 96 ... 111, the costliest fits of
-// a 100-iteration run), which brings the CTA to 90 KB of shared memory so that two of them share an SM
+// the staging buffer is walked in NCH chunks: two for the 16 x 16 grid at NB = 6, 7 (n = 80 ... 111, the costliest fits
+// of a 100-iteration run), which brings the CTA to 68 / 90 KB of shared memory so that three / two of them share an SM
 template <int NB, int OW>
-__host__ __device__ constexpr int fit_kchunks() { return (OW == 16 && NB == 7) ? 2 : 1; }
+__host__ __device__ constexpr int fit_kchunks() { return (OW == 16 && (NB == 6 || NB == 7)) ? 2 : 1; }
 template <int NB, int OW>
 __host__ __device__ constexpr int fit_kchunk_slots() { return (NB * (NB + 1) / 2 + fit_kchunks<NB, OW>() - 1) / fit_kchunks<NB, OW>(); }
 
@@ -370,7 +370,7 @@ __device__ __forceinline__ void fit_load_trial(const FitSmem& s, const double* _
 
 // ---- K-C: one evaluation per trial ------------------------------------------------------------------------
 template <int NB, int OW>
-__global__ void __launch_bounds__(OW * OW, (OW == 8 ? 1 : (NB <= 7 ? 2 : 1)))
+__global__ void __launch_bounds__(OW * OW, (OW == 8 ? 1 : (NB <= 6 ? 3 : (NB <= 7 ? 2 : 1))))
 mll_sweep_kernel(const double* __restrict__ X, const double* __restrict__ y, const int32_t* __restrict__ n_arr,
                  const double* __restrict__ raw, double* __restrict__ value, double* __restrict__ grad,
                  int32_t* __restrict__ status, int n_max, int kernel_id) {
@@ -403,7 +403,7 @@ mll_sweep_kernel(const double* __restrict__ X, const double* __restrict__ y, con
 // and its gradient, lets thread 0 advance the L-BFGS state machine (lbfgs.cuh) and repeats until the trial
 // converges: one launch per fit, and nobody waits for the slowest trial of the batch between evaluations.
 template <int NB, int OW>
-__global__ void __launch_bounds__(OW * OW, (OW == 8 ? 1 : (NB <= 7 ? 2 : 1)))
+__global__ void __launch_bounds__(OW * OW, (OW == 8 ? 1 : (NB <= 6 ? 3 : (NB <= 7 ? 2 : 1))))
 gp_fit_sweep_kernel(const double* __restrict__ X, const double* __restrict__ y, const int32_t* __restrict__ n_arr,
                     const double* __restrict__ raw0, int raw0_per_trial, double* __restrict__ theta_out,
                     double* __restrict__ raw_out, double* __restrict__ mll_out, int32_t* __restrict__ iters_out,
