@@ -127,7 +127,6 @@ gp_chol_kernel(const double* __restrict__ X, const double* __restrict__ y, const
   }
   CholSmem s = carve(sm, n_cap, ld);
   __shared__ double red[CH_THREADS / 32];
-  __shared__ double sh_scalar[8];
 
   const double* th = theta + (size_t)t * 4;
   const double noise = th[0], cst = th[1], sc = th[2], ell = th[3];
@@ -170,7 +169,6 @@ gp_chol_kernel(const double* __restrict__ X, const double* __restrict__ y, const
   if (threadIdx.x == 0) {
     double tsum = 0.0;
     for (int w = 0; w < CH_THREADS / 32; ++w) tsum += red[w];
-    sh_scalar[0] = 2.0 * tsum;
     if (logdet_out) logdet_out[t] = 2.0 * tsum;
   }
   if (L_out) {
