@@ -136,7 +136,7 @@ struct GridAcqParams {
 template <int KID, int NI_MAX, bool LATTICE, int CH, int MINB, int NT>
 __global__ void __launch_bounds__(GA_THREADS, MINB)
 grid_acq_kernel(const GridAcqParams p) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const int t = blockIdx.x / p.chunks;
   const int chunk = blockIdx.x - t * p.chunks;
   const int n = p.n[t];
@@ -392,7 +392,7 @@ template <int NI, int THREADS>
 __global__ void __launch_bounds__(THREADS, (THREADS == 128 ? (NI <= 8 ? KB_MINB_SMALL : 4) : (THREADS == 256 ? 2 : 1)))
 grid_acq_lattice_kernel(const GridAcqParams p) {
   constexpr int NWARPS = THREADS / 32;
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const int t = blockIdx.x / p.chunks;
   const int chunk = blockIdx.x - t * p.chunks;
   const int n = p.n[t];
@@ -415,10 +415,14 @@ grid_acq_lattice_kernel(const GridAcqParams p) {
   __shared__ double red_val[NWARPS];
   __shared__ int red_idx[NWARPS];
   __shared__ int red_flag;
+  __shared__ __align__(8) unsigned long long stage_bar;
   {
-    const double2* src = reinterpret_cast<const double2*>(p.wfrag + (size_t)t * p.wstride);
-    double2* dst = reinterpret_cast<double2*>(wsm);
-    for (int e = threadIdx.x; e < nblk * 16; e += THREADS) dst[e] = src[e];
+    // L^-1 fragments of this trial: one contiguous, 256-byte granular range (prefix property of the fragment layout)
+    // -> ONE bulk copy through the TMA unit (cp.async.bulk + mbarrier), issued by thread 0 while the other threads
+    // decode the observation coordinates
+    if (threadIdx.x == 0) mbar_init(&stage_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) tma_bulk_g2s(wsm, p.wfrag + (size_t)t * p.wstride, (unsigned)nblk * 256u, &stage_bar);
     for (int j = threadIdx.x; j < npad; j += THREADS) {
       const bool v = j < n;
       const double x = v ? p.X[((size_t)t * p.n_max + j) * 2] : p.x0;
@@ -437,6 +441,7 @@ grid_acq_lattice_kernel(const GridAcqParams p) {
   const double sc = p.theta[(size_t)t * 4 + 2];
   const double best_f = p.best_f[t];
   __syncthreads();
+  mbar_wait(&stage_bar, 0);               // the staged fragments have landed
 
   const int col0 = chunk * p.cols_per_cta;
   const int col_end = min(p.G, col0 + p.cols_per_cta);
