@@ -45,7 +45,7 @@ class LBFGSFitter:
         p, s = ops._ptr, ops._stream()
         T = self.T
         if self.fused:
-            # one launch: every trial runs its own L-BFGS to convergence inside its CTA (csrc/gp_chol.cu:gp_fit_kernel)
+            # one launch: every trial runs its own L-BFGS to convergence inside its CTA (csrc/gp_fit.cu:gp_fit_sweep_kernel)
             check(lib.b200bo_gp_fit(p(X), p(y), p(n), p(self.raw0), self.raw0_per_trial, p(theta_out), p(self.raw),
                                     p(self.mll), p(self.iters), p(status if status is not None else self.kc_status), T,
                                     y.shape[1], int(n_hint), int(kernel_id), NOISE_LB, self.gtol, self.ftol, self.max_iter,

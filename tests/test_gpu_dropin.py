@@ -244,7 +244,7 @@ def test_single_call_entry_points(golden):
 
 
 def test_fused_fit_kernel_equals_round_based_fit(golden, lattice_grid):
-    """gp_fit_kernel (one launch, one CTA per trial) runs the same optimiser on the same arithmetic as the
+    """gp_fit_sweep_kernel (one launch, one CTA per trial) runs the same optimiser on the same arithmetic as the
     mll_value_grad + lbfgs_step rounds: identical optimum, iteration and evaluation counts."""
     from b200bo import fit
     dev = torch.device("cuda:0")
