@@ -29,6 +29,12 @@
 #ifndef KB_MU2
 #define KB_MU2 0             // 1: two interleaved accumulators for the posterior-mean dot product
 #endif
+#ifndef KB8_MINB_MID
+#define KB8_MINB_MID 5       // byte-coordinate tile, 128-thread CTAs, 6 <= NI <= 8: CTAs/SM target (measured: 5 beats 4 by 1-3 %)
+#endif
+#ifndef KB_ABLATE
+#define KB_ABLATE 0          // timing experiments ONLY (results are wrong when non-zero): bit 0 = no table look-ups,
+#endif                       // bit 1 = L^-1 fragment from a register instead of shared memory, bit 2 = no acquisition
 
 namespace b200bo {
 
@@ -348,13 +354,16 @@ __device__ __forceinline__ void lattice_tile(const double* __restrict__ wsm, con
 #pragma unroll
   for (int I = 0; I < NI; ++I) { acc[I][0] = 0.0; acc[I][1] = 0.0; }
   auto index_of = [&](int J) {
+    if (KB_ABLATE & 1) return J;
     const int pk = xyi[4 * J + jrow];
     const int dxi = abs(gxi - (pk & 0xffff)), dyi = abs(gyi - (pk >> 16));
     return dyi * Gx + dxi;
   };
   // software pipeline: table values two k-blocks ahead
   int ix0 = index_of(0), ix1 = index_of(1);
-  double kv0 = __ldg(tab + ix0), kv1 = __ldg(tab + ix1);
+  auto look_up = [&](int ix) { return (KB_ABLATE & 1) ? (double)(ix + gxi) : __ldg(tab + ix); };
+  const double a_reg = (KB_ABLATE & 2) ? wsm[lane] : 0.0;
+  double kv0 = look_up(ix0), kv1 = look_up(ix1);
   mu_part = 0.0;
   double mu_odd = 0.0;
   masked = 0;
@@ -366,7 +375,7 @@ __device__ __forceinline__ void lattice_tile(const double* __restrict__ wsm, con
     kv0 = kv1; ix0 = ix1;
     if (J + 2 < NJ && (EXACT || J + 2 < 2 * nI)) {
       ix1 = index_of(J + 2);
-      kv1 = __ldg(tab + ix1);
+      kv1 = look_up(ix1);
     }
     // padded observations (j >= n) meet zero columns of L^-1 and alpha = 0: any finite value is harmless
     masked |= (ix == 0 && 4 * J + jrow < n) ? 1 : 0;       // dxi < Gx, so index 0 <=> the observed point itself
@@ -375,7 +384,7 @@ __device__ __forceinline__ void lattice_tile(const double* __restrict__ wsm, con
 #pragma unroll
     for (int I = J / 2; I < NI; ++I) {
       if (EXACT || I < nI)
-        dmma_m8n8k4(acc[I][0], acc[I][1], wsm[(size_t)(I * (I + 1) + J) * 32 + lane], kv);
+        dmma_m8n8k4(acc[I][0], acc[I][1], (KB_ABLATE & 2) ? __hiloint2double(__double2hiint(a_reg) ^ (I + 1), __double2loint(a_reg)) : wsm[(size_t)(I * (I + 1) + J) * 32 + lane], kv);
     }
   }
   if (KB_MU2) mu_part += mu_odd;
@@ -503,6 +512,229 @@ grid_acq_lattice_kernel(const GridAcqParams p) {
       if (p.mu_out) p.mu_out[(size_t)t * p.G + g] = mu;
       if (p.var_out) p.var_out[(size_t)t * p.G + g] = var;
       const double d = mu - best_f;
+      const bool skip = (KB_ABLATE & 4) ? (var > -1e300) : (prune && wbest > 0.0 && d < 0.0 && 0.5 * d * d > fmax(var, p.var_floor) * lthr);
+      if (!skip) {
+        double a;
+        if (p.acq_id == B200BO_ACQ_UCB) a = acquisition<B200BO_ACQ_UCB>(mu, var, best_f, p.acq_param, p.var_floor);
+        else if (p.acq_id == B200BO_ACQ_PI) a = acquisition<B200BO_ACQ_PI>(mu, var, best_f, p.acq_param, p.var_floor);
+        else a = acquisition<B200BO_ACQ_EI>(mu, var, best_f, p.acq_param, p.var_floor);
+        if (p.acq_out) p.acq_out[(size_t)t * p.G + g] = a;
+        if (!m) {
+          if (isnan(a) || a == INFINITY) flags |= B200BO_ST_NONFINITE;
+          if (!isnan(a) && better(a, g, best_v, best_i)) { best_v = a; best_i = g; }
+        }
+      }
+    }
+  }
+  warp_argmax(best_v, best_i);
+  flags = __reduce_or_sync(0xffffffffu, flags);
+  if (lane == 0) {
+    red_val[warp] = best_v;
+    red_idx[warp] = best_i;
+    if (flags) atomicOr(&red_flag, flags);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double bv = red_val[0];
+    int bi = red_idx[0];
+    for (int w = 1; w < NWARPS; ++w)
+      if (better(red_val[w], red_idx[w], bv, bi)) { bv = red_val[w]; bi = red_idx[w]; }
+    p.part_val[(size_t)t * p.chunks + chunk] = bv;
+    p.part_idx[(size_t)t * p.chunks + chunk] = bi;
+    if (red_flag && p.status) atomicOr(&p.status[t], red_flag);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Lattice K-B, byte-coordinate variant (production path when 8 <= Gx <= 255 and Gy <= 256, i.e. every lattice the
+// reference uses: 100x100 and 200x200).
+//
+// Ablation on the GPU (profiles/README.md, "K-B ablation") showed that the time of a column tile is, to within 1-2 %,
+//     16 cycles x #DMMA  +  1 cycle x #other warp-instructions        (per SM sub-partition)
+// i.e. instruction issue does not overlap with the FP64 MMA pipe, shared-memory bandwidth is NOT a limiter, and every
+// integer instruction around the MMAs costs pipe time. The generic-lattice tile above spends ~18 instructions per table
+// look-up (unpack, two subtracts, two IABS, IMAD, 4-instruction 64-bit address, mask compares, alpha LDS + DFMA).
+// Here:
+//   * coordinates are packed one byte each (x | y << 8): |dx|, |dy| come from ONE VABSDIFF4 and the table index
+//     |dy| Gx + |dx| from ONE IDP.4A against the byte weights (1, Gx) — then IMAD.WIDE + LDG: 4 instructions;
+//   * observations and alpha are stored per k-row (lane & 3), so one LDS.128 fetches the coordinates of four k-blocks
+//     and one LDS.128 two alpha values;
+//   * "candidate is an observed point" comes from a per-CTA bit mask built while staging (one broadcast LDS per 32
+//     candidates) instead of two compares per look-up and a shuffle reduction per tile;
+//   * the candidate's (gx, gy) is divided out once per 32 candidates and stepped by 8 per tile.
+// Same table, same indices, same summation order as lattice_tile -> bit-identical results.
+template <int NI, bool EXACT>
+__device__ __forceinline__ void lattice_tile8(const double* __restrict__ wsm, const uint4* __restrict__ xyq,
+                                              const double2* __restrict__ alq, const double* __restrict__ tab,
+                                              unsigned wpk, unsigned cpk, int lane, int nI, double& ss0, double& ss1,
+                                              double& mu_part) {
+  constexpr int NJ = 2 * NI;
+  double acc[NI][2];
+#pragma unroll
+  for (int I = 0; I < NI; ++I) { acc[I][0] = 0.0; acc[I][1] = 0.0; }
+  auto look_up = [&](unsigned pk) { return __ldg(tab + __dp4a(__vabsdiffu4(cpk, pk), wpk, 0u)); };
+  uint4 pq = xyq[0];                                       // observations of k-blocks 0..3 (this lane's k-row)
+  double kv0 = look_up(pq.x), kv1 = look_up(pq.y);         // software pipeline: table values two k-blocks ahead
+  double2 a2 = make_double2(0.0, 0.0);
+  mu_part = 0.0;
+#pragma unroll
+  for (int J = 0; J < NJ; ++J) {
+    if (!EXACT && J >= 2 * nI) break;                      // uniform
+    const double kv = kv0;
+    kv0 = kv1;
+    if (J + 2 < NJ && (EXACT || J + 2 < 2 * nI)) {
+      if ((J + 2) % 4 == 0) pq = xyq[(J + 2) / 4];
+      kv1 = look_up((J + 2) % 4 == 0 ? pq.x : (J + 2) % 4 == 1 ? pq.y : (J + 2) % 4 == 2 ? pq.z : pq.w);
+    }
+    if (J % 2 == 0) a2 = alq[J / 2];
+    // padded observations (j >= n) meet zero columns of L^-1 and alpha = 0: any finite value is harmless
+    mu_part = fma(kv, (J % 2 == 0) ? a2.x : a2.y, mu_part);
+#pragma unroll
+    for (int I = J / 2; I < NI; ++I) {
+      if (EXACT || I < nI) dmma_m8n8k4(acc[I][0], acc[I][1], wsm[(size_t)(I * (I + 1) + J) * 32 + lane], kv);
+    }
+  }
+  ss0 = 0.0;
+  ss1 = 0.0;
+#pragma unroll
+  for (int I = 0; I < NI; ++I) {
+    ss0 = fma(acc[I][0], acc[I][0], ss0);
+    ss1 = fma(acc[I][1], acc[I][1], ss1);
+  }
+}
+
+// per-k-row strides of the alpha / coordinate arrays in 16-byte units, made ODD so that the four k-rows of a warp's
+// LDS.128 fall into distinct bank groups (a 128-byte stride - NI = 8 - would be a 4-way conflict)
+template <int NI> __host__ __device__ constexpr int lattice8_al_stride() { return NI | 1; }                  // double2 units (>= NJ / 2)
+template <int NI> __host__ __device__ constexpr int lattice8_xy_stride() { return ((2 * NI + 3) / 4) | 1; }  // uint4 units (>= NJ / 4)
+
+template <int NI>
+__host__ __device__ constexpr size_t lattice8_fixed_smem() {
+  return (size_t)NI * (NI + 1) * 32 * sizeof(double) + 4 * (size_t)(lattice8_al_stride<NI>() + lattice8_xy_stride<NI>()) * 16;
+}
+
+template <int NI, int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS == 128 ? (NI <= 5 ? KB_MINB_SMALL : (NI <= 8 ? KB8_MINB_MID : 4)) : (THREADS == 256 ? 2 : 1)))
+grid_acq_lattice8_kernel(const GridAcqParams p) {
+  constexpr int NWARPS = THREADS / 32;
+  constexpr int ALS = 2 * lattice8_al_stride<NI>();   // alpha row stride in doubles
+  constexpr int XYS = 4 * lattice8_xy_stride<NI>();   // coordinate row stride in 32-bit words
+  extern __shared__ __align__(16) double sm[];
+  const int t = blockIdx.x / p.chunks;
+  const int chunk = blockIdx.x - t * p.chunks;
+  const int n = p.n[t];
+  if (n <= 0) return;                     // finished / inactive trial (uniform per CTA)
+  if (n > p.n_cap || n > 8 * NI) {        // n_hint too small: report, do not touch memory
+    if (threadIdx.x == 0) {
+      p.part_val[(size_t)t * p.chunks + chunk] = -INFINITY;
+      p.part_idx[(size_t)t * p.chunks + chunk] = INT_MAX;
+      if (p.status) atomicOr(&p.status[t], B200BO_ST_ALL_MASKED);
+    }
+    return;
+  }
+  const int nI = (n + 7) >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nblk = nI * (nI + 1);
+  const int col0 = chunk * p.cols_per_cta;
+  const int col_end = min(p.G, col0 + p.cols_per_cta);
+  double* wsm = sm;                                                    // NI (NI + 1) * 32
+  double* alT = sm + (size_t)NI * (NI + 1) * 32;                       // [4][ALS]: alpha of observation 4 J + k-row
+  unsigned* xyT = reinterpret_cast<unsigned*>(alT + 4 * ALS);          // [4][XYS]: x | y << 8 of the same observation
+  unsigned* obsbits = xyT + 4 * XYS;                                   // bit (g - col0): candidate g is an observed point
+  __shared__ double red_val[NWARPS];
+  __shared__ int red_idx[NWARPS];
+  __shared__ int red_flag;
+  __shared__ __align__(8) unsigned long long stage_bar;
+  {
+    if (threadIdx.x == 0) mbar_init(&stage_bar, 1);
+    for (int w = threadIdx.x; w < (p.cols_per_cta >> 5); w += THREADS) obsbits[w] = 0u;
+    __syncthreads();
+    // L^-1 fragments: one contiguous, 256-byte granular range -> ONE bulk copy through the TMA unit
+    if (threadIdx.x == 0) tma_bulk_g2s(wsm, p.wfrag + (size_t)t * p.wstride, (unsigned)nblk * 256u, &stage_bar);
+    for (int j = threadIdx.x; j < 4 * XYS; j += THREADS) {
+      const bool v = j < n;
+      const double x = v ? p.X[((size_t)t * p.n_max + j) * 2] : p.x0;
+      const double y = v ? p.X[((size_t)t * p.n_max + j) * 2 + 1] : p.y0;
+      const double fx = rint((x - p.x0) / p.h), fy = rint((y - p.y0) / p.h);
+      const bool on = (p.x0 + p.h * fx == x) && (p.y0 + p.h * fy == y) && fx >= 0.0 && fy >= 0.0 &&
+                      fx < (double)p.Gx && fy < (double)p.Gy;
+      const int xi = on ? (int)fx : 0, yi = on ? (int)fy : 0;
+      xyT[(j & 3) * XYS + (j >> 2)] = (unsigned)xi | ((unsigned)yi << 8);
+      if (j < 4 * ALS) alT[(j & 3) * ALS + (j >> 2)] = v ? p.alpha[(size_t)t * p.n_max + j] : 0.0;
+      if (v && !on && p.status) atomicOr(&p.status[t], B200BO_ST_OFF_LATTICE);
+      if (v && on && p.mask_observed) {
+        const int gflat = yi * p.Gx + xi;
+        if (gflat >= col0 && gflat < col_end) atomicOr(&obsbits[(gflat - col0) >> 5], 1u << ((gflat - col0) & 31));
+      }
+    }
+    if (threadIdx.x == 0) red_flag = 0;
+  }
+  const double* tab = p.ktab + (size_t)(p.ktab_id ? p.ktab_id[t] : 0) * p.Gx * p.Gy;
+  // keep base + slot offset as ONE 64-bit register pair: the look-up address is then a single IMAD.WIDE (left to
+  // itself the compiler re-adds the uniform slot offset per look-up: IADD3 + IMAD.X + LEA + LEA.HI.X)
+  asm volatile("" : "+l"(tab));
+  const double cst = p.theta[(size_t)t * 4 + 1];
+  const double sc = p.theta[(size_t)t * 4 + 2];
+  const double best_f = p.best_f[t];
+  __syncthreads();
+  mbar_wait(&stage_bar, 0);               // the staged fragments have landed
+
+  const int jrow = lane & 3, bcol = lane >> 2;
+  const uint4* xyq = reinterpret_cast<const uint4*>(xyT + jrow * XYS);
+  const double2* alq = reinterpret_cast<const double2*>(alT + jrow * ALS);
+  const unsigned wpk = 1u | ((unsigned)p.Gx << 8);
+  double best_v = -INFINITY;
+  int best_i = INT_MAX;
+  int flags = 0;
+  const bool prune = p.acq_id == B200BO_ACQ_EI && p.acq_out == nullptr && p.prune;
+  double wbest = 0.0, lthr = INFINITY;
+
+  for (int base = col0 + warp * 32; base < col_end; base += NWARPS * 32) {
+    double my_ss = 0.0, my_mu = 0.0;
+    // lattice coordinates of this lane's candidate in tile 0; later tiles step x by 8 (Gx >= 8). Candidates past
+    // G - 1 stay inside the table (their results are discarded below).
+    int gyi = (base + bcol) / p.Gx, gxi = (base + bcol) - gyi * p.Gx;
+    gyi = min(gyi, p.Gy - 1);
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+      const unsigned cpk = (unsigned)gxi | ((unsigned)gyi << 8);
+      double ss0, ss1, mp;
+      if (nI == NI) lattice_tile8<NI, true>(wsm, xyq, alq, tab, wpk, cpk, lane, nI, ss0, ss1, mp);
+      else lattice_tile8<NI, false>(wsm, xyq, alq, tab, wpk, cpk, lane, nI, ss0, ss1, mp);
+      gxi += 8;
+      if (gxi >= p.Gx) { gxi -= p.Gx; gyi = min(gyi + 1, p.Gy - 1); }
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {                  // rows live in lane>>2
+        ss0 += __shfl_xor_sync(0xffffffffu, ss0, o);
+        ss1 += __shfl_xor_sync(0xffffffffu, ss1, o);
+      }
+#pragma unroll
+      for (int o = 1; o < 4; o <<= 1) mp += __shfl_xor_sync(0xffffffffu, mp, o);   // k-rows live in lane&3
+      const int cc = lane & 7;                            // hand column cc of this tile to lane 8q + cc
+      const double t0 = __shfl_sync(0xffffffffu, ss0, cc >> 1);
+      const double t1 = __shfl_sync(0xffffffffu, ss1, cc >> 1);
+      const double tm = __shfl_sync(0xffffffffu, mp, cc * 4);
+      if ((lane >> 3) == q) {
+        my_ss = (cc & 1) ? t1 : t0;
+        my_mu = tm;
+      }
+    }
+    const int g = base + lane;
+    const bool my_masked = (obsbits[(base - col0) >> 5] >> lane) & 1u;
+    if (prune) {                                          // EI pruning (exact): see grid_acq_lattice_kernel
+      const double nb = warp_max(best_v);
+      if (nb > wbest) {                                   // uniform
+        wbest = nb;
+        lthr = log(kInvSqrt2Pi * sqrt(sc) / nb) * (1.0 + 1e-12) + 1e-12;
+      }
+    }
+    if (g < col_end) {
+      const double mu = cst + my_mu;
+      const double var = sc - my_ss;
+      const bool m = my_masked || (p.extra_mask && p.extra_mask[g]);
+      if (p.mu_out) p.mu_out[(size_t)t * p.G + g] = mu;
+      if (p.var_out) p.var_out[(size_t)t * p.G + g] = var;
+      const double d = mu - best_f;
       const bool skip = prune && wbest > 0.0 && d < 0.0 && 0.5 * d * d > fmax(var, p.var_floor) * lthr;
       if (!skip) {
         double a;
@@ -537,6 +769,17 @@ grid_acq_lattice_kernel(const GridAcqParams p) {
 }
 
 template <int NI, int THREADS>
+static int launch_lattice8_t(const GridAcqParams& p, int T, cudaStream_t st) {
+  const size_t smem = lattice8_fixed_smem<NI>() + (size_t)(p.cols_per_cta >> 5) * sizeof(unsigned);
+  // the mask grows with the column chunk (5 KB for a whole 200x200 lattice): set the limit once, to the largest case
+  cudaError_t e = cudaFuncSetAttribute(grid_acq_lattice8_kernel<NI, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(lattice8_fixed_smem<NI>() + 8320));
+  if (e != cudaSuccess) return cuda_status(e, "grid_posterior_acq_argmax_lattice: smem attribute");
+  grid_acq_lattice8_kernel<NI, THREADS><<<(unsigned)((size_t)T * p.chunks), THREADS, smem, st>>>(p);
+  return 0;
+}
+
+template <int NI, int THREADS>
 static int launch_lattice_t(const GridAcqParams& p, int T, cudaStream_t st) {
   size_t smem = ((size_t)NI * (NI + 1) * 32 + 8 * (size_t)NI) * sizeof(double) + 8 * (size_t)NI * sizeof(int);
   cudaError_t e = cudaFuncSetAttribute(grid_acq_lattice_kernel<NI, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -552,6 +795,13 @@ static int launch_lattice(const GridAcqParams& p, int T, cudaStream_t st) {
   // Measured (tools/perf_probe.py): n = 110: 0.80 -> 0.85 of FP64 peak; n <= 64: 128 threads are better.
   static const int thr = env_int("B200BO_KB_THREADS", 0);
   const int use = thr ? thr : (NI >= 9 ? 256 : 128);
+  // byte-coordinate tile (VABSDIFF4 + IDP.4A look-ups, observed-point bit mask) whenever the lattice fits one byte per
+  // axis and the mask fits the reserved shared memory; B200BO_KB_BYTE=0 forces the general tile (A/B runs)
+  static const int byte_ok = env_int("B200BO_KB_BYTE", 1);
+  if (byte_ok && p.Gx >= 8 && p.Gx <= 255 && p.Gy <= 256 && (p.cols_per_cta >> 5) * sizeof(unsigned) <= 8320) {
+    if (use == 256) return launch_lattice8_t<NI, 256>(p, T, st);
+    return launch_lattice8_t<NI, 128>(p, T, st);
+  }
   if (use == 256) return launch_lattice_t<NI, 256>(p, T, st);
   return launch_lattice_t<NI, 128>(p, T, st);
 }

@@ -207,6 +207,46 @@ def test_lattice_variant_is_bit_identical_to_generic(golden, lattice_grid, kid):
         assert torch.equal(a[key], b[key]), key
 
 
+@pytest.mark.parametrize("shape", [(8, 40), (13, 37), (255, 20), (100, 256), (300, 12), (7, 50)])
+def test_lattice_tiles_on_odd_shapes_equal_generic(shape):
+    """Byte-coordinate tile (8 <= Gx <= 255, Gy <= 256: packed |dx|,|dy| look-ups, observed-point bit mask, x stepped by 8
+    per tile with row wrap) and the general tile (other shapes) against the generic kernel: bit-identical fields, index and
+    status, including masked observed candidates, several column chunks per trial and a ragged last tile."""
+    from b200bo import ops
+    Gx, Gy = shape
+    h, x0, y0 = 0.5, -3.0, 2.0
+    gx, gy = np.meshgrid(x0 + h * np.arange(Gx), y0 + h * np.arange(Gy))
+    grid_h = np.stack([gx, gy], axis=-1).reshape(-1, 2)
+    G = Gx * Gy
+    rng = np.random.default_rng(Gx * 1000 + Gy)
+    n_list = [3, 17, 40]
+    T, n_max = len(n_list), 40
+    X = np.zeros((T, n_max, 2)); y = np.zeros((T, n_max)); n = np.array(n_list, dtype=np.int32)
+    for t in range(T):
+        pick = rng.choice(G, n[t], replace=False)
+        pick[0] = G - 1                                  # an observed point in the ragged last tile
+        X[t, :n[t]] = grid_h[pick]
+        y[t, :n[t]] = rng.uniform(0, 100, n[t])
+    th = np.tile(np.array([0.05, 40.0, 150.0, 4.0]), (T, 1))
+    st = ops.gp_assemble_chol(_to(X), _to(y), _to(n), _to(th), 3)
+    best = np.array([y[t, :n[t]].max() for t in range(T)])
+    grid = _to(grid_h)
+    lat = ops.Lattice.from_points(grid)
+    assert (lat.Gx, lat.Gy) == (Gx, Gy)
+    ktab = ops.kernel_table(_to(th[:1]), 3, lat)
+    a = ops.grid_posterior_acq_argmax(grid, _to(X), st["wfrag"], st["alpha"], _to(n), _to(th), _to(best), 3, debug=True)
+    b = ops.grid_posterior_acq_argmax_lattice(lat, ktab, None, _to(X), st["wfrag"], st["alpha"], _to(n), _to(th), _to(best), 3,
+                                              debug=True)
+    for key in ("mu", "var", "acq", "idx", "val", "status"):
+        assert torch.equal(a[key], b[key]), key
+    # no debug fields: the pruned production path picks the same candidate
+    c = ops.grid_posterior_acq_argmax_lattice(lat, ktab, None, _to(X), st["wfrag"], st["alpha"], _to(n), _to(th), _to(best), 3)
+    assert torch.equal(c["idx"], a["idx"])
+    # an observed point must never be picked
+    for t in range(T):
+        assert not np.any(np.all(X[t, :n[t]] == grid_h[int(a["idx"][t])], axis=1))
+
+
 def test_lattice_half_step_grid_and_off_lattice_flag(golden):
     """constructX(budget=40000): 200x200 nodes, step 0.5 (BASELINE config 4 candidates)."""
     from b200bo import ops
