@@ -293,7 +293,7 @@ def run_b200(args):
     kb_avg_ms = kb_ms / max(1, len(kb))
     roofline = {"bound": "tensor", "bound_detail": "FP64 tensor pipe: mma.sync.m8n8k4.f64 (DMMA), which shares the SM's FP64 "
                                                    "pipe with DFMA (profiles/fp64_peaks_r1.json); not HBM (see hbm_view)",
-                "kernel": "grid_acq_lattice_kernel<NI> (K-B)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "kernel": "grid_acq_lattice8_kernel<NI,THREADS> (K-B, byte-coordinate lattice tile)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak if peak else None, "traffic": traffic,
                 "hbm_view": {"algorithmic_bytes_per_launch_mean": float(np.mean([T * (8 * ops.wfrag_doubles(n) + 24 * n + 56) for n, _ in kb])) if kb else None,
                              "achieved_gbs": (float(np.mean([T * (8 * ops.wfrag_doubles(n) + 24 * n + 56) for n, _ in kb])) / (kb_avg_ms * 1e-3) / 1e9) if kb else None,
