@@ -688,6 +688,11 @@ grid_acq_lattice8_kernel(const GridAcqParams p) {
   int flags = 0;
   const bool prune = p.acq_id == B200BO_ACQ_EI && p.acq_out == nullptr && p.prune;
   double wbest = 0.0, lthr = INFINITY;
+  // per-warp stack of candidates that survived the pruning test (64 entries: at most 31 left + 32 pushed)
+  double* q_mu = reinterpret_cast<double*>(obsbits + (p.cols_per_cta >> 5)) + warp * 128;
+  double* q_var = q_mu + 64;
+  int* q_g = reinterpret_cast<int*>(reinterpret_cast<double*>(obsbits + (p.cols_per_cta >> 5)) + NWARPS * 128) + warp * 64;
+  int qn = 0;
 
   for (int base = col0 + warp * 32; base < col_end; base += NWARPS * 32) {
     double my_ss = 0.0, my_mu = 0.0;
@@ -721,32 +726,65 @@ grid_acq_lattice8_kernel(const GridAcqParams p) {
     }
     const int g = base + lane;
     const bool my_masked = (obsbits[(base - col0) >> 5] >> lane) & 1u;
-    if (prune) {                                          // EI pruning (exact): see grid_acq_lattice_kernel
-      const double nb = warp_max(best_v);
-      if (nb > wbest) {                                   // uniform
-        wbest = nb;
-        lthr = log(kInvSqrt2Pi * sqrt(sc) / nb) * (1.0 + 1e-12) + 1e-12;
-      }
-    }
-    if (g < col_end) {
-      const double mu = cst + my_mu;
-      const double var = sc - my_ss;
-      const bool m = my_masked || (p.extra_mask && p.extra_mask[g]);
+    const double mu = cst + my_mu;
+    const double var = sc - my_ss;
+    const bool live = g < col_end;
+    const bool m = my_masked || (p.extra_mask && live && p.extra_mask[g]);
+    if (live) {
       if (p.mu_out) p.mu_out[(size_t)t * p.G + g] = mu;
       if (p.var_out) p.var_out[(size_t)t * p.G + g] = var;
+    }
+    if (prune) {
+      // EI with exact pruning and warp-level compaction. For mu < best_f, EI = sigma phi(u) + (mu - best_f) Phi(u)
+      // <= 0.39894 sqrt(s) exp(-u^2 / 2) because the posterior sigma never exceeds the prior sqrt(s): a candidate whose
+      // bound is below the warp's running maximum can neither win nor tie, so its sqrt / exp / erfc (~160 FP64-pipe
+      // slots) are skipped; the test is two multiplies. Survivors are not evaluated in place (one surviving lane would
+      // make the whole warp walk the EI code) but pushed on a per-warp stack in shared memory and evaluated 32 at a
+      // time with full lanes; the threshold is refreshed after each batch (a stale threshold only prunes less).
       const double d = mu - best_f;
-      const bool skip = prune && wbest > 0.0 && d < 0.0 && 0.5 * d * d > fmax(var, p.var_floor) * lthr;
-      if (!skip) {
-        double a;
-        if (p.acq_id == B200BO_ACQ_UCB) a = acquisition<B200BO_ACQ_UCB>(mu, var, best_f, p.acq_param, p.var_floor);
-        else if (p.acq_id == B200BO_ACQ_PI) a = acquisition<B200BO_ACQ_PI>(mu, var, best_f, p.acq_param, p.var_floor);
-        else a = acquisition<B200BO_ACQ_EI>(mu, var, best_f, p.acq_param, p.var_floor);
-        if (p.acq_out) p.acq_out[(size_t)t * p.G + g] = a;
-        if (!m) {
+      const bool skip = wbest > 0.0 && d < 0.0 && 0.5 * d * d > fmax(var, p.var_floor) * lthr;
+      const bool need = live && !m && !skip;
+      const unsigned bal = __ballot_sync(0xffffffffu, need);
+      if (bal) {                                          // uniform
+        if (need) {
+          const int pos = qn + __popc(bal & ((1u << lane) - 1u));
+          q_mu[pos] = mu; q_var[pos] = var; q_g[pos] = g;
+        }
+        qn += __popc(bal);
+        if (qn >= 32) {
+          __syncwarp();
+          qn -= 32;
+          const double a = acquisition<B200BO_ACQ_EI>(q_mu[qn + lane], q_var[qn + lane], best_f, p.acq_param, p.var_floor);
+          const int ga = q_g[qn + lane];
           if (isnan(a) || a == INFINITY) flags |= B200BO_ST_NONFINITE;
-          if (!isnan(a) && better(a, g, best_v, best_i)) { best_v = a; best_i = g; }
+          if (!isnan(a) && better(a, ga, best_v, best_i)) { best_v = a; best_i = ga; }
+          __syncwarp();
+          const double nb = warp_max(best_v);
+          if (nb > wbest) {                               // uniform
+            wbest = nb;
+            lthr = log(kInvSqrt2Pi * sqrt(sc) / nb) * (1.0 + 1e-12) + 1e-12;
+          }
         }
       }
+    } else if (live) {
+      double a;
+      if (p.acq_id == B200BO_ACQ_UCB) a = acquisition<B200BO_ACQ_UCB>(mu, var, best_f, p.acq_param, p.var_floor);
+      else if (p.acq_id == B200BO_ACQ_PI) a = acquisition<B200BO_ACQ_PI>(mu, var, best_f, p.acq_param, p.var_floor);
+      else a = acquisition<B200BO_ACQ_EI>(mu, var, best_f, p.acq_param, p.var_floor);
+      if (p.acq_out) p.acq_out[(size_t)t * p.G + g] = a;
+      if (!m) {
+        if (isnan(a) || a == INFINITY) flags |= B200BO_ST_NONFINITE;
+        if (!isnan(a) && better(a, g, best_v, best_i)) { best_v = a; best_i = g; }
+      }
+    }
+  }
+  if (prune && qn > 0) {                                  // the rest of the stack (qn < 32)
+    __syncwarp();
+    if (lane < qn) {
+      const double a = acquisition<B200BO_ACQ_EI>(q_mu[lane], q_var[lane], best_f, p.acq_param, p.var_floor);
+      const int ga = q_g[lane];
+      if (isnan(a) || a == INFINITY) flags |= B200BO_ST_NONFINITE;
+      if (!isnan(a) && better(a, ga, best_v, best_i)) { best_v = a; best_i = ga; }
     }
   }
   warp_argmax(best_v, best_i);
@@ -770,10 +808,11 @@ grid_acq_lattice8_kernel(const GridAcqParams p) {
 
 template <int NI, int THREADS>
 static int launch_lattice8_t(const GridAcqParams& p, int T, cudaStream_t st) {
-  const size_t smem = lattice8_fixed_smem<NI>() + (size_t)(p.cols_per_cta >> 5) * sizeof(unsigned);
+  constexpr size_t stack_bytes = (size_t)(THREADS / 32) * 64 * (2 * sizeof(double) + sizeof(int));   // survivors' stacks
+  const size_t smem = lattice8_fixed_smem<NI>() + (size_t)(p.cols_per_cta >> 5) * sizeof(unsigned) + stack_bytes;
   // the mask grows with the column chunk (5 KB for a whole 200x200 lattice): set the limit once, to the largest case
   cudaError_t e = cudaFuncSetAttribute(grid_acq_lattice8_kernel<NI, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(lattice8_fixed_smem<NI>() + 8320));
+                                       (int)(lattice8_fixed_smem<NI>() + 8320 + stack_bytes));
   if (e != cudaSuccess) return cuda_status(e, "grid_posterior_acq_argmax_lattice: smem attribute");
   grid_acq_lattice8_kernel<NI, THREADS><<<(unsigned)((size_t)T * p.chunks), THREADS, smem, st>>>(p);
   return 0;
@@ -860,7 +899,10 @@ void launch_argmax_finish(const double* part_val, const int32_t* part_idx, int c
 
 inline int pick_chunks(int T, int G) {
   int max_chunks = (G + GA_THREADS - 1) / GA_THREADS;
-  int want = (4 * 148 + T - 1) / T;
+  // CTAs per launch >= waves x (148 SMs x 4 CTAs): a trial's columns are split until the last, partially filled wave
+  // of CTAs is a small share of the launch (B200BO_KB_WAVES, default 1 = one CTA per trial once T >= 592)
+  static const int waves = env_int("B200BO_KB_WAVES", 1);
+  int want = (waves * 4 * 148 + T - 1) / T;
   if (want < 1) want = 1;
   return want > max_chunks ? max_chunks : want;
 }
