@@ -32,6 +32,9 @@
 #ifndef KB8_MINB_MID
 #define KB8_MINB_MID 5       // byte-coordinate tile, 128-thread CTAs, 6 <= NI <= 8: CTAs/SM target (measured: 5 beats 4 by 1-3 %)
 #endif
+#ifndef KB8_TAIL
+#define KB8_TAIL 1           // byte-coordinate tile: 1..2 live rows of the last row block by DFMA instead of DMMA
+#endif
 #ifndef KB_ABLATE
 #define KB_ABLATE 0          // timing experiments ONLY (results are wrong when non-zero): bit 0 = no table look-ups,
 #endif                       // bit 1 = L^-1 fragment from a register instead of shared memory, bit 2 = no acquisition
@@ -563,20 +566,32 @@ grid_acq_lattice_kernel(const GridAcqParams p) {
 //     candidates) instead of two compares per look-up and a shuffle reduction per tile;
 //   * the candidate's (gx, gy) is divided out once per 32 candidates and stepped by 8 per tile.
 // Same table, same indices, same summation order as lattice_tile -> bit-identical results.
-template <int NI, bool EXACT>
+// TAIL (2, only with EXACT): the last row block holds r = n - 8 (NI - 1) <= TAIL live rows. A DMMA spends the
+// same 16 cycles on it as on a full block (2 NI of the tile's NI (NI + 1) MMAs for one or two rows), so those rows are
+// taken off the MMA path: row rho of the block is a per-lane DFMA chain over the lane's own k-row (the L^-1 entry is a
+// 4-address broadcast LDS from the same fragment block), summed over the four k-row lanes at the end of the tile.
+// 2.75 cycles per (row, k-block) instead of 16 per k-block; the last k-block (columns >= 8 NI - 4 >= n) is not
+// needed at all. Rows r..TAIL-1 are zero in the fragment block and add nothing.
+template <int NI, bool EXACT, int TAIL>
 __device__ __forceinline__ void lattice_tile8(const double* __restrict__ wsm, const uint4* __restrict__ xyq,
                                               const double2* __restrict__ alq, const double* __restrict__ tab,
                                               unsigned wpk, unsigned cpk, int lane, int nI, double& ss0, double& ss1,
-                                              double& mu_part) {
-  constexpr int NJ = 2 * NI;
-  double acc[NI][2];
+                                              double& mu_part, double& tail_ss) {
+  static_assert(TAIL == 0 || EXACT, "tail rows only for full-size trials");
+  constexpr int ND = TAIL ? NI - 1 : NI;                   // row blocks on the MMA path
+  constexpr int NJ = TAIL ? 2 * NI - 1 : 2 * NI;           // k-blocks that can hold a non-zero column
+  double acc[ND > 0 ? ND : 1][2];
+  double tl[TAIL > 0 ? TAIL : 1];
 #pragma unroll
-  for (int I = 0; I < NI; ++I) { acc[I][0] = 0.0; acc[I][1] = 0.0; }
+  for (int I = 0; I < ND; ++I) { acc[I][0] = 0.0; acc[I][1] = 0.0; }
+#pragma unroll
+  for (int r = 0; r < TAIL; ++r) tl[r] = 0.0;
   auto look_up = [&](unsigned pk) { return __ldg(tab + __dp4a(__vabsdiffu4(cpk, pk), wpk, 0u)); };
   uint4 pq = xyq[0];                                       // observations of k-blocks 0..3 (this lane's k-row)
   double kv0 = look_up(pq.x), kv1 = look_up(pq.y);         // software pipeline: table values two k-blocks ahead
   double2 a2 = make_double2(0.0, 0.0);
   mu_part = 0.0;
+  const double* wtail = wsm + (size_t)(NI - 1) * NI * 32 + (lane & 3);
 #pragma unroll
   for (int J = 0; J < NJ; ++J) {
     if (!EXACT && J >= 2 * nI) break;                      // uniform
@@ -590,16 +605,26 @@ __device__ __forceinline__ void lattice_tile8(const double* __restrict__ wsm, co
     // padded observations (j >= n) meet zero columns of L^-1 and alpha = 0: any finite value is harmless
     mu_part = fma(kv, (J % 2 == 0) ? a2.x : a2.y, mu_part);
 #pragma unroll
-    for (int I = J / 2; I < NI; ++I) {
+    for (int I = J / 2; I < ND; ++I) {
       if (EXACT || I < nI) dmma_m8n8k4(acc[I][0], acc[I][1], wsm[(size_t)(I * (I + 1) + J) * 32 + lane], kv);
     }
+#pragma unroll
+    for (int r = 0; r < TAIL; ++r) tl[r] = fma(wtail[J * 32 + 4 * r], kv, tl[r]);
   }
   ss0 = 0.0;
   ss1 = 0.0;
 #pragma unroll
-  for (int I = 0; I < NI; ++I) {
+  for (int I = 0; I < ND; ++I) {
     ss0 = fma(acc[I][0], acc[I][0], ss0);
     ss1 = fma(acc[I][1], acc[I][1], ss1);
+  }
+  tail_ss = 0.0;
+#pragma unroll
+  for (int r = 0; r < TAIL; ++r) {                         // v of row 8 (NI - 1) + r for candidate lane >> 2
+    double v = tl[r];
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    tail_ss = fma(v, v, tail_ss);
   }
 }
 
@@ -693,6 +718,10 @@ grid_acq_lattice8_kernel(const GridAcqParams p) {
   double* q_var = q_mu + 64;
   int* q_g = reinterpret_cast<int*>(reinterpret_cast<double*>(obsbits + (p.cols_per_cta >> 5)) + NWARPS * 128) + warp * 64;
   int qn = 0;
+  // one or two live rows in the last row block leave the MMA path (lattice_tile8, TAIL = 2): measured -5..-7 % per
+  // launch at n = 8k + 1, 8k + 2. Four DFMA rows (n = 8k + 3, 8k + 4) were measured too and LOSE 2..20 %: not built.
+  static_assert(KB8_TAIL == 0 || KB8_TAIL == 1, "KB8_TAIL is a switch");
+  const int tail_rows = (KB8_TAIL && nI == NI && n - 8 * (NI - 1) <= 2) ? 2 : 0;
 
   for (int base = col0 + warp * 32; base < col_end; base += NWARPS * 32) {
     double my_ss = 0.0, my_mu = 0.0;
@@ -703,9 +732,10 @@ grid_acq_lattice8_kernel(const GridAcqParams p) {
 #pragma unroll 1
     for (int q = 0; q < 4; ++q) {
       const unsigned cpk = (unsigned)gxi | ((unsigned)gyi << 8);
-      double ss0, ss1, mp;
-      if (nI == NI) lattice_tile8<NI, true>(wsm, xyq, alq, tab, wpk, cpk, lane, nI, ss0, ss1, mp);
-      else lattice_tile8<NI, false>(wsm, xyq, alq, tab, wpk, cpk, lane, nI, ss0, ss1, mp);
+      double ss0, ss1, mp, tq;
+      if (tail_rows == 2) lattice_tile8<NI, true, 2>(wsm, xyq, alq, tab, wpk, cpk, lane, nI, ss0, ss1, mp, tq);
+      else if (nI == NI) lattice_tile8<NI, true, 0>(wsm, xyq, alq, tab, wpk, cpk, lane, nI, ss0, ss1, mp, tq);
+      else lattice_tile8<NI, false, 0>(wsm, xyq, alq, tab, wpk, cpk, lane, nI, ss0, ss1, mp, tq);
       gxi += 8;
       if (gxi >= p.Gx) { gxi -= p.Gx; gyi = min(gyi + 1, p.Gy - 1); }
 #pragma unroll
@@ -719,8 +749,9 @@ grid_acq_lattice8_kernel(const GridAcqParams p) {
       const double t0 = __shfl_sync(0xffffffffu, ss0, cc >> 1);
       const double t1 = __shfl_sync(0xffffffffu, ss1, cc >> 1);
       const double tm = __shfl_sync(0xffffffffu, mp, cc * 4);
+      const double tt = tail_rows ? __shfl_sync(0xffffffffu, tq, cc * 4) : 0.0;
       if ((lane >> 3) == q) {
-        my_ss = (cc & 1) ? t1 : t0;
+        my_ss = ((cc & 1) ? t1 : t0) + tt;
         my_mu = tm;
       }
     }

@@ -247,6 +247,45 @@ def test_lattice_tiles_on_odd_shapes_equal_generic(shape):
         assert not np.any(np.all(X[t, :n[t]] == grid_h[int(a["idx"][t])], axis=1))
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 9, 10, 11, 12, 13, 34, 44, 65, 68, 97, 100, 105, 121, 124])
+def test_lattice_tail_rows_off_the_mma_path(lattice_grid, n):
+    """Uniform batches whose last row block holds 1..2 live rows: the byte-coordinate tile takes those rows off the DMMA
+    path (per-lane DFMA chains), so var may differ from the generic kernel in the last bits — bounded here by 1e-13 s
+    (mu is computed identically); the pick must be the same unless the two best acquisition values tie to 1e-12."""
+    from b200bo import ops
+    T = 4
+    rng = np.random.default_rng(n)
+    G = lattice_grid.shape[0]
+    X = np.zeros((T, n, 2)); y = np.zeros((T, n))
+    for t in range(T):
+        X[t] = lattice_grid[rng.choice(G, n, replace=False)]
+        y[t] = 40 + 25 * np.sin(X[t, :, 0] / 9.0) * np.cos(X[t, :, 1] / 13.0) + rng.normal(0, 0.5, n)
+    nn = np.full(T, n, dtype=np.int32)
+    th = np.tile(_theta(), (T, 1))
+    st = ops.gp_assemble_chol(_to(X), _to(y), _to(nn), _to(th), 3)
+    best = y.max(axis=1)
+    grid = _to(lattice_grid)
+    lat = ops.Lattice.from_points(grid)
+    ktab = ops.kernel_table(_to(th[:1]), 3, lat)
+    a = ops.grid_posterior_acq_argmax(grid, _to(X), st["wfrag"], st["alpha"], _to(nn), _to(th), _to(best), 3, debug=True)
+    b = ops.grid_posterior_acq_argmax_lattice(lat, ktab, None, _to(X), st["wfrag"], st["alpha"], _to(nn), _to(th), _to(best), 3,
+                                              debug=True)
+    c = ops.grid_posterior_acq_argmax_lattice(lat, ktab, None, _to(X), st["wfrag"], st["alpha"], _to(nn), _to(th), _to(best), 3)
+    assert torch.equal(a["mu"], b["mu"]) and torch.equal(a["status"], b["status"])
+    s = th[0, 2]
+    assert float((a["var"] - b["var"]).abs().max()) <= 1e-13 * s
+    if (n - 1) % 8 >= 2:                                 # 3..8 live rows: everything stays on the MMA path
+        assert torch.equal(a["var"], b["var"]) and torch.equal(a["acq"], b["acq"])
+    for t in range(T):
+        ia, ib, ic = int(a["idx"][t]), int(b["idx"][t]), int(c["idx"][t])
+        acq = a["acq"][t]
+        assert ib == ic
+        if ia != ib:
+            assert abs(float(acq[ia] - acq[ib])) <= 1e-12 * abs(float(acq[ia]))
+        idx, val, sto, mu, var, aq = ogp.grid_step(lattice_grid, X[t], y[t], th[t], 3, return_fields=True)
+        assert np.allclose(b["var"][t].cpu().numpy(), var, rtol=1e-8, atol=1e-10 * s)
+
+
 def test_lattice_half_step_grid_and_off_lattice_flag(golden):
     """constructX(budget=40000): 200x200 nodes, step 0.5 (BASELINE config 4 candidates)."""
     from b200bo import ops
