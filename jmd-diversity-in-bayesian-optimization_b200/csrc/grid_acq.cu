@@ -32,6 +32,9 @@
 #ifndef KB8_MINB_MID
 #define KB8_MINB_MID 5       // byte-coordinate tile, 128-thread CTAs, 6 <= NI <= 8: CTAs/SM target (measured: 5 beats 4 by 1-3 %)
 #endif
+#ifndef KB8_RS_MAX_NI
+#define KB8_RS_MAX_NI 4      // byte-coordinate tile: reduce-scatter epilogue over four tiles up to this many row blocks
+#endif
 #ifndef KB8_TAIL
 #define KB8_TAIL 1           // byte-coordinate tile: 1..2 live rows of the last row block by DFMA instead of DMMA
 #endif
@@ -722,13 +725,24 @@ grid_acq_lattice8_kernel(const GridAcqParams p) {
   // launch at n = 8k + 1, 8k + 2. Four DFMA rows (n = 8k + 3, 8k + 4) were measured too and LOSE 2..20 %: not built.
   static_assert(KB8_TAIL == 0 || KB8_TAIL == 1, "KB8_TAIL is a switch");
   const int tail_rows = (KB8_TAIL && nI == NI && n - 8 * (NI - 1) <= 2) ? 2 : 0;
+  const int j0 = lane & 1, j1 = (lane >> 1) & 1, b0 = (lane >> 2) & 1, b1 = (lane >> 3) & 1, b2 = lane >> 4;
 
   for (int base = col0 + warp * 32; base < col_end; base += NWARPS * 32) {
-    double my_ss = 0.0, my_mu = 0.0;
     // lattice coordinates of this lane's candidate in tile 0; later tiles step x by 8 (Gx >= 8). Candidates past
     // G - 1 stay inside the table (their results are discarded below).
     int gyi = (base + bcol) / p.Gx, gxi = (base + bcol) - gyi * p.Gx;
     gyi = min(gyi, p.Gy - 1);
+    // Reduction of the four tiles' partial sums as a reduce-scatter: the shuffles share the LSU data pipe with the
+    // fragment loads and the table gathers, and that pipe is 85-89 % busy at n <= 32 (ncu). A butterfly per tile moves
+    // 44 words per tile through it; here every exchange halves the number of values a lane keeps (8 column sums over
+    // the 8 row lanes: xor 4, 8, 16; 4 mean sums over the 4 k-row lanes: xor 1, 2), 22-24 words per FOUR tiles, and
+    // each lane ends with exactly one candidate. The pairing order equals the butterfly's (same partner at every
+    // level, fp add is commutative), so the sums are bit-identical to it.
+    // (Measured: +4..13 % at n <= 24, nothing at n = 32..48, -1 % from n = 64 on, where the six values kept across
+    // tiles cost registers — so the reduce-scatter serves NI <= KB8_RS_MAX_NI and the per-tile butterfly the rest.)
+    constexpr bool RS = NI <= KB8_RS_MAX_NI;
+    double w_even = 0.0, m_even = 0.0, t_even = 0.0, u0 = 0.0, mu0 = 0.0, tt0 = 0.0;
+    double ssF = 0.0, muF = 0.0, ttF = 0.0;
 #pragma unroll 1
     for (int q = 0; q < 4; ++q) {
       const unsigned cpk = (unsigned)gxi | ((unsigned)gyi << 8);
@@ -738,25 +752,53 @@ grid_acq_lattice8_kernel(const GridAcqParams p) {
       else lattice_tile8<NI, false, 0>(wsm, xyq, alq, tab, wpk, cpk, lane, nI, ss0, ss1, mp, tq);
       gxi += 8;
       if (gxi >= p.Gx) { gxi -= p.Gx; gyi = min(gyi + 1, p.Gy - 1); }
+      if constexpr (RS) {
+        // level 1 (row lanes xor 4): keep column 2 jrow + b0 of this tile
+        const double w = (b0 ? ss1 : ss0) + __shfl_xor_sync(0xffffffffu, b0 ? ss0 : ss1, 4);
+        if (!(q & 1)) {                                     // uniform
+          w_even = w; m_even = mp; t_even = tq;
+        } else {
+          // level 2 (xor 8): keep tile 2 (q / 2) + b1; mean level 1 (k-row lanes xor 1): keep tile 2 (q / 2) + j0
+          const double u = (b1 ? w : w_even) + __shfl_xor_sync(0xffffffffu, b1 ? w_even : w, 8);
+          const double mm = (j0 ? mp : m_even) + __shfl_xor_sync(0xffffffffu, j0 ? m_even : mp, 1);
+          const double tt = j0 ? tq : t_even;
+          if (q == 1) {
+            u0 = u; mu0 = mm; tt0 = tt;
+          } else {
+            // level 3 (xor 16): keep tile pair b2; mean level 2 (xor 2): keep tile pair j1
+            ssF = (b2 ? u : u0) + __shfl_xor_sync(0xffffffffu, b2 ? u0 : u, 16);
+            muF = (j1 ? mm : mu0) + __shfl_xor_sync(0xffffffffu, j1 ? mu0 : mm, 2);
+            ttF = j1 ? tt : tt0;
+          }
+        }
+      } else {
 #pragma unroll
-      for (int o = 4; o < 32; o <<= 1) {                  // rows live in lane>>2
-        ss0 += __shfl_xor_sync(0xffffffffu, ss0, o);
-        ss1 += __shfl_xor_sync(0xffffffffu, ss1, o);
-      }
+        for (int o = 4; o < 32; o <<= 1) {                  // rows live in lane>>2
+          ss0 += __shfl_xor_sync(0xffffffffu, ss0, o);
+          ss1 += __shfl_xor_sync(0xffffffffu, ss1, o);
+        }
 #pragma unroll
-      for (int o = 1; o < 4; o <<= 1) mp += __shfl_xor_sync(0xffffffffu, mp, o);   // k-rows live in lane&3
-      const int cc = lane & 7;                            // hand column cc of this tile to lane 8q + cc
-      const double t0 = __shfl_sync(0xffffffffu, ss0, cc >> 1);
-      const double t1 = __shfl_sync(0xffffffffu, ss1, cc >> 1);
-      const double tm = __shfl_sync(0xffffffffu, mp, cc * 4);
-      const double tt = tail_rows ? __shfl_sync(0xffffffffu, tq, cc * 4) : 0.0;
-      if ((lane >> 3) == q) {
-        my_ss = ((cc & 1) ? t1 : t0) + tt;
-        my_mu = tm;
+        for (int o = 1; o < 4; o <<= 1) mp += __shfl_xor_sync(0xffffffffu, mp, o);   // k-rows live in lane&3
+        const int cc = lane & 7;                            // hand column cc of this tile to lane 8q + cc
+        const double t0 = __shfl_sync(0xffffffffu, ss0, cc >> 1);
+        const double t1 = __shfl_sync(0xffffffffu, ss1, cc >> 1);
+        const double tm = __shfl_sync(0xffffffffu, mp, cc * 4);
+        const double tt = tail_rows ? __shfl_sync(0xffffffffu, tq, cc * 4) : 0.0;
+        if ((lane >> 3) == q) {
+          ssF = ((cc & 1) ? t1 : t0) + tt;
+          muF = tm;
+        }
       }
     }
-    const int g = base + lane;
-    const bool my_masked = (obsbits[(base - col0) >> 5] >> lane) & 1u;
+    // reduce-scatter: this lane holds the column sum of candidate off = 8 (2 b2 + b1) + 4 j1 + 2 j0 + b0 of the
+    // super-tile; its mean (and tail sum) sit on the lane with column bits (j1, j0, b0) as row lane and tile bits
+    // (b2, b1) as k-row lane. Butterfly: lane l holds candidate l.
+    const int src = 4 * (4 * j1 + 2 * j0 + b0) + 2 * b2 + b1;
+    const double my_mu = RS ? __shfl_sync(0xffffffffu, muF, src) : muF;
+    const double my_ss = RS ? ssF + (tail_rows ? __shfl_sync(0xffffffffu, ttF, src) : 0.0) : ssF;
+    const int off = RS ? 8 * (2 * b2 + b1) + 4 * j1 + 2 * j0 + b0 : lane;
+    const int g = base + off;
+    const bool my_masked = (obsbits[(base - col0) >> 5] >> off) & 1u;
     const double mu = cst + my_mu;
     const double var = sc - my_ss;
     const bool live = g < col_end;
