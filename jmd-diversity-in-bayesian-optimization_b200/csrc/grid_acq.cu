@@ -970,14 +970,44 @@ void launch_argmax_finish(const double* part_val, const int32_t* part_idx, int c
   argmax_finish_kernel<<<(T + 127) / 128, 128, 0, st>>>(part_val, part_idx, chunks, T, n, arg_idx, arg_val, status);
 }
 
-inline int pick_chunks(int T, int G) {
-  int max_chunks = (G + GA_THREADS - 1) / GA_THREADS;
-  // CTAs per launch >= waves x (148 SMs x 4 CTAs): a trial's columns are split until the last, partially filled wave
-  // of CTAs is a small share of the launch (B200BO_KB_WAVES, default 1 = one CTA per trial once T >= 592)
+// Column chunks per trial. A launch has T x chunks CTAs for `slots` resident CTAs (148 SMs x CTAs per SM of the
+// instantiation): first enough chunks to fill the GPU once, then up to 15 more when that shortens the last, partially
+// filled wave — e.g. 1 000 trials on 740 slots: 1 chunk = 2 waves for 1.35 waves of work, 5 chunks = 7 waves for 6.76.
+// Every extra chunk re-stages L^-1 and restarts the pruning threshold (~1 % each, measured with B200BO_KB_WAVES); 2 % per
+// chunk is charged in the cost, so large batches (T >> slots) keep one CTA per trial.
+inline int max_chunks_of(int G) { return (G + GA_THREADS - 1) / GA_THREADS; }
+
+inline int pick_chunks(int T, int G, int slots) {
+  static const int waves = env_int("B200BO_KB_WAVES", 1);   // experiments: force at least this many waves
+  const int max_chunks = max_chunks_of(G);
+  int lo = (int)(((long long)waves * slots + T - 1) / T);
+  if (lo < 1) lo = 1;
+  if (lo > max_chunks) lo = max_chunks;
+  int best = lo;
+  double best_cost = 1e300;
+  for (int c = lo; c <= max_chunks && c < lo + 16; ++c) {
+    const long long ctas = (long long)T * c;
+    const double cost = (double)((ctas + slots - 1) / slots) / c * (1.0 + 0.02 * (c - lo));
+    if (cost < best_cost - 1e-12) { best_cost = cost; best = c; }
+  }
+  return best;
+}
+
+// upper bound of pick_chunks over every instantiation (workspace sizing; at most 6 CTAs per SM)
+inline int max_pick_chunks(int T, int G) {
   static const int waves = env_int("B200BO_KB_WAVES", 1);
-  int want = (waves * 4 * 148 + T - 1) / T;
-  if (want < 1) want = 1;
-  return want > max_chunks ? max_chunks : want;
+  long long lo = ((long long)waves * 148 * 6 + T - 1) / T;
+  long long hi = lo + 16;
+  const int max_chunks = max_chunks_of(G);
+  return (int)(hi > max_chunks ? max_chunks : hi);
+}
+
+// resident CTAs per SM of the kernel a launch with n_cap observations will take (launch bounds / shared memory)
+inline int kb_ctas_per_sm(bool lattice, int n_cap) {
+  const int nI = (n_cap + 7) / 8;
+  if (!lattice) return nI <= 8 ? 4 : 3;
+  if (nI >= 9) return 2;                 // 256-thread CTAs
+  return nI <= 5 ? KB_MINB_SMALL : KB8_MINB_MID;
 }
 
 inline size_t grid_acq_smem(int nI) {
@@ -1042,7 +1072,7 @@ extern "C" {
 
 size_t b200bo_grid_acq_workspace_bytes(int T, int G) {
   if (T <= 0 || G <= 0) return 0;
-  int chunks = b200bo::pick_chunks(T, G);
+  int chunks = b200bo::max_pick_chunks(T, G);
   return (size_t)T * chunks * (sizeof(double) + sizeof(int32_t)) + 16;
 }
 
@@ -1076,7 +1106,8 @@ static int grid_acq_common(bool lattice, const double* grid, int G, int Gx, int 
   p.acq_id = acq_id;
   p.acq_param = acq_id == B200BO_ACQ_UCB ? sqrt(acq_param) : acq_param;
   p.var_floor = var_floor;
-  p.chunks = pick_chunks(T, G);
+  p.n_cap = (n_hint > 0 && n_hint < n_max) ? n_hint : n_max;
+  p.chunks = pick_chunks(T, G, 148 * kb_ctas_per_sm(lattice, p.n_cap));
   p.prune = env_int("B200BO_KB_PRUNE", 1);
   p.cols_per_cta = (((G + p.chunks - 1) / p.chunks + GA_THREADS - 1) / GA_THREADS) * GA_THREADS;
   p.part_val = reinterpret_cast<double*>(ws);
