@@ -388,7 +388,7 @@ def bench_other_configs(dev, surf, S):
     out = {}
     rng = np.random.default_rng(99)
 
-    def run(name, lat, T, iters, theta, tol, reps=1):
+    def run(name, lat, T, iters, theta, tol, reps=1, groups=1):
         G = lat.G
         pts = lat.points(dev)
         if lat.h == 1.0:
@@ -400,27 +400,39 @@ def bench_other_configs(dev, surf, S):
         sid = torch.as_tensor((np.arange(T) % S).astype(np.int32), device=dev)
         X0 = pts[idx]
         y0 = obj[sid.long()[:, None], idx].double()
-        fitter = None if theta is not None else fit.LBFGSFitter(T, dev)
-        bo = engine.BatchedBO(pts, obj, sid, X0, y0, iters, theta=theta, tol=tol, fitter=fitter, lattice=lat)
-        bo.run()                                                   # warm-up
+        # groups > 1: the batch cut into contiguous groups advanced concurrently on separate CUDA streams
+        # (engine.run_concurrent; same results trial by trial)
+        cuts = [T * g // groups for g in range(groups + 1)]
+        bos = []
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            fitter = None if theta is not None else fit.LBFGSFitter(hi - lo, dev)
+            bos.append(engine.BatchedBO(pts, obj, sid[lo:hi], X0[lo:hi], y0[lo:hi], iters, theta=theta, tol=tol,
+                                        fitter=fitter, lattice=lat))
+        streams = [torch.cuda.Stream(dev) for _ in bos]
+        go = (lambda: [bos[0].run()]) if groups == 1 else (lambda: engine.run_concurrent(bos, streams))
+        go()                                                       # warm-up
         torch.cuda.synchronize(dev)
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
-            bo.reset(X0, y0)
-            res = bo.run()
+            for bo, lo, hi in zip(bos, cuts[:-1], cuts[1:]):
+                bo.reset(X0[lo:hi], y0[lo:hi])
+            res = engine.concat_results(go())
         e1.record()
         torch.cuda.synchronize(dev)
         sec = e0.elapsed_time(e1) * 1e-3 / reps
         nit = int(res.nit.sum().item())
         out[name] = {"trials": T, "grid": f"{lat.Gx}x{lat.Gy}", "iterations_max": iters, "tol": tol, "seconds": sec,
-                     "bo_iterations": nit, "bo_iterations_per_s": nit / sec, "status_bits": int(res.status.max().item())}
-        if fitter is not None:
-            out[name]["fit_evaluations_mean_last"] = float(fitter.iters[:, 1].float().mean().item())
+                     "bo_iterations": nit, "bo_iterations_per_s": nit / sec, "status_bits": int(res.status.max().item()),
+                     "concurrent_groups": groups}
+        if theta is None:
+            out[name]["fit_evaluations_mean_last"] = float(torch.cat([b.fitter.iters[:, 1] for b in bos]).float().mean().item())
 
     theta = torch.tensor(THETA, dtype=torch.float64, device=dev)
     run("configs[2]_fit_every_iteration_tol_disabled", ops.Lattice(100, 100), 1000, 100, None, -1.0)
     run("configs[2]_fit_every_iteration_tol_0.1", ops.Lattice(100, 100), 1000, 100, None, 0.1)
+    run("configs[2]_fit_every_iteration_tol_disabled_3_streams", ops.Lattice(100, 100), 1000, 100, None, -1.0, groups=3)
+    run("configs[2]_fit_every_iteration_tol_0.1_3_streams", ops.Lattice(100, 100), 1000, 100, None, 0.1, groups=3)
     run("configs[3]_grid200_fixed_theta_slice", ops.Lattice(200, 200, 0.0, 0.0, 0.5), 1184, 100, theta, -1.0)
     # configs[0]: ONE BO run through the reference-facing API (optimizer.optimize -> BOloop_fixparam), 10 initial
     # points, fixed theta, EI over the 100 x 100 lattice, 50 iterations — latency of a single trial, wall clock

@@ -207,10 +207,13 @@ def _fixparam_to_theta(fixparam):
 
 def BOloop_batched(obj_tables, surf_id, init_X, init_y, max_iter, theta=None, grid=None, acq="EI", acq_param=0.0,
                    tol=0.1, optimal_y=100.0, nu=2.5, covar="matern", device="cuda:0", lattice="auto", theta_rest=None,
-                   posterior="full"):
+                   posterior="full", groups="auto"):
     """Native batched entry: T trials in lock-step. obj_tables (S,G) f32 objective at every candidate, surf_id (T,),
     init_X (T,n0,2), init_y (T,n0); theta (4,) / (T,4) ACTUAL hyper-parameters or None (= fit before every
     acquisition). posterior="incremental" (fixed theta, lattice candidates): O(n) posterior update per candidate. grid: (G,2) candidates or an ops.Lattice (default: the 100x100 lattice of data_gen.constructX).
+    groups > 1 cuts the batch into that many contiguous groups advanced concurrently on separate CUDA streams (same
+    results trial by trial; pays when theta is None and the per-iteration fit has a long tail: b200bo.engine.run_concurrent);
+    "auto" = 3 groups for fitted batches of at least 384 trials, else 1.
     Returns b200bo.engine.BOResult (device tensors)."""
     dev = torch.device(device)
     t = lambda a, dt: torch.as_tensor(a, dtype=dt).to(dev).contiguous()
@@ -220,13 +223,26 @@ def BOloop_batched(obj_tables, surf_id, init_X, init_y, max_iter, theta=None, gr
     pts = grid.points(dev) if isinstance(grid, ops.Lattice) else t(grid, torch.float64)
     T = np.shape(init_y)[0]
     acq_id = {"EI": ops.EI, "UCB": ops.UCB, "PI": ops.PI}[acq]
-    fitter = None if theta is not None else fit.LBFGSFitter(T, dev)
-    bo = engine.BatchedBO(pts, t(obj_tables, torch.float32), t(surf_id, torch.int32), t(init_X, torch.float64),
-                          t(init_y, torch.float64), max_iter, theta=None if theta is None else t(theta, torch.float64),
-                          kernel_id=ops.kernel_id_from(nu, covar), acq_id=acq_id, acq_param=acq_param, tol=tol,
-                          optimal_y=optimal_y, fitter=fitter, lattice=lat,
-                          theta_rest=None if theta_rest is None else t(theta_rest, torch.float64), posterior=posterior)
-    return bo.run()
+    obj_d, sid_d = t(obj_tables, torch.float32), t(surf_id, torch.int32)
+    X_d, y_d = t(init_X, torch.float64), t(init_y, torch.float64)
+    th_d = None if theta is None else t(theta, torch.float64)
+    rest_d = None if theta_rest is None else t(theta_rest, torch.float64)
+
+    def make(lo, hi):
+        sub = lambda a: a if a is None or a.dim() == 1 and a.shape[0] == 4 else a[lo:hi]
+        fitter = None if theta is not None else fit.LBFGSFitter(hi - lo, dev)
+        return engine.BatchedBO(pts, obj_d, sid_d[lo:hi], X_d[lo:hi], y_d[lo:hi], max_iter, theta=sub(th_d),
+                                kernel_id=ops.kernel_id_from(nu, covar), acq_id=acq_id, acq_param=acq_param, tol=tol,
+                                optimal_y=optimal_y, fitter=fitter, lattice=lat, theta_rest=sub(rest_d),
+                                posterior=posterior)
+
+    if groups == "auto":                                   # measured on 1 000 / 4 000 trials: +8..22 % with a fit per iteration
+        groups = 3 if (theta is None and T >= 384) else 1
+    groups = max(1, min(int(groups), T))
+    if groups == 1:
+        return make(0, T).run()
+    cuts = [T * g // groups for g in range(groups + 1)]
+    return engine.concat_results(engine.run_concurrent([make(cuts[g], cuts[g + 1]) for g in range(groups)]))
 
 
 def _single(obj_func, max_iter, X, Y, theta, bounds, tol, nu, covar, minstate, optimal_y, budget, device,

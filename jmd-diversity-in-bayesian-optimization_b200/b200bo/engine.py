@@ -245,18 +245,75 @@ class BatchedBO:
         self._graph.replay()
         return self._graph_result
 
-    def run(self) -> BOResult:
+    def _begin(self):
         ops.bo_init(self.y, self.n, self.best_f, self.yall, self.picked, self.nit, self.max_iter, self.tol, self.optimal_y)
         self.launches += 1
-        for it in range(self.max_iter):
-            if self.incremental:
-                self._step_incremental(it)
-            else:
-                self.step(it)
-            if self.check_every and (it + 1) % self.check_every == 0 and it + 1 < self.max_iter:
-                if not bool((self.n > 0).any()):        # every trial reached tol: stop enqueueing
-                    break
+
+    def _advance(self, it: int):
+        if self.incremental:
+            self._step_incremental(it)
+        else:
+            self.step(it)
+
+    def _end(self) -> BOResult:
         ops.bo_finalize(self.yall, self.nit, self.n, self.max_iter)
         self.launches += 1
         return BOResult(self.yall, self.picked[:, :self.max_iter], self.nit, self.status, self.X, self.y, self.n,
                         self.thetas)
+
+    def run(self) -> BOResult:
+        self._begin()
+        for it in range(self.max_iter):
+            self._advance(it)
+            if self.check_every and (it + 1) % self.check_every == 0 and it + 1 < self.max_iter:
+                if not bool((self.n > 0).any()):        # every trial reached tol: stop enqueueing
+                    break
+        return self._end()
+
+
+def run_concurrent(bos, streams=None):
+    """Advance several independent BatchedBO batches from one host thread, each on its own CUDA stream.
+
+    Trials never exchange data (the reference runs them as separate processes, Scripts/Experiment2.py:83-91), so a batch
+    may be cut anywhere. With a fit before every acquisition the per-iteration kernels of ONE batch end with a long
+    tail — the fused fit runs until its slowest trial has converged while most CTAs have already left — and on
+    separate streams the tail of one group overlaps the bulk of the next. Results are those of the single-batch run,
+    trial by trial (tests/test_gpu_bo_loop.py::test_concurrent_groups_equal_one_batch). Returns one BOResult per batch."""
+    if not bos:
+        return []
+    dev = bos[0].grid.device
+    cur = torch.cuda.current_stream(dev)
+    if streams is None:
+        streams = [torch.cuda.Stream(dev) for _ in bos]
+    for s in streams:
+        s.wait_stream(cur)                              # buffers were initialised on the caller's stream
+    max_iter = max(bo.max_iter for bo in bos)
+    check_every = min((bo.check_every for bo in bos if bo.check_every), default=0)
+    for bo, s in zip(bos, streams):
+        with torch.cuda.stream(s):
+            bo._begin()
+    for it in range(max_iter):
+        for bo, s in zip(bos, streams):
+            if it < bo.max_iter:
+                with torch.cuda.stream(s):
+                    bo._advance(it)
+        if check_every and (it + 1) % check_every == 0 and it + 1 < max_iter:
+            alive = False
+            for bo, s in zip(bos, streams):
+                with torch.cuda.stream(s):
+                    alive = alive or bool((bo.n > 0).any())
+            if not alive:
+                break
+    out = []
+    for bo, s in zip(bos, streams):
+        with torch.cuda.stream(s):
+            out.append(bo._end())
+        cur.wait_stream(s)
+    return out
+
+
+def concat_results(results) -> BOResult:
+    """One BOResult from the per-group results of run_concurrent (same max_iter and n_max in every group)."""
+    cat = lambda name: torch.cat([getattr(r, name) for r in results], dim=0)
+    thetas = None if results[0].thetas is None else cat("thetas")
+    return BOResult(cat("yall"), cat("picked"), cat("nit"), cat("status"), cat("X"), cat("y"), cat("n"), thetas)

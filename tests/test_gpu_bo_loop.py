@@ -170,3 +170,20 @@ def test_cuda_graph_replay_equals_eager_run(golden, lattice_grid, fit_mode):
         torch.cuda.synchronize()
         assert torch.equal(rg.picked, re_.picked) and torch.equal(rg.yall, re_.yall) and torch.equal(rg.nit, re_.nit)
         X0, y0 = sets()
+
+
+@pytest.mark.parametrize("fit_mode", [False, True])
+def test_concurrent_groups_equal_one_batch(golden, lattice_grid, fit_mode):
+    """BOloop_batched(groups=3): the batch cut into three groups advanced on separate CUDA streams returns, trial by
+    trial, bit for bit what the single batch returns (trials are independent; engine.run_concurrent)."""
+    import BO
+    T, n0, max_iter = 23, 10, 12
+    obj, surf_id, X0, y0 = _setup(golden, lattice_grid, T, n0, seed=5)
+    theta = None if fit_mode else ogp.raw_to_theta(AUTHOR_THETA_RAW)
+    a = BO.BOloop_batched(obj, surf_id, X0, y0, max_iter, theta=theta, tol=0.1, device=DEV)
+    b = BO.BOloop_batched(obj, surf_id, X0, y0, max_iter, theta=theta, tol=0.1, device=DEV, groups=3)
+    torch.cuda.synchronize()
+    for name in ("yall", "picked", "nit", "status", "X", "y", "n"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    if fit_mode:
+        assert torch.equal(a.thetas, b.thetas)
