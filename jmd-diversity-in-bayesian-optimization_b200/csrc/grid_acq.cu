@@ -1029,25 +1029,22 @@ static int launch_grid_acq_v(const GridAcqParams& p, int T, cudaStream_t st) {
   return 0;
 }
 
-// tuning switch for experiments (B200BO_KB_TILES = 1|2 column tiles per MMA group); default = measured best
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
 }
 
-template <int KID, int NI_MAX, bool LATTICE>
+// generic kernel: two accumulator chains per row-block group, one column tile per MMA group (measured best)
+template <int KID, int NI_MAX>
 static int launch_grid_acq(const GridAcqParams& p, int T, cudaStream_t st) {
-  static const int tiles = env_int("B200BO_KB_TILES", 1);
-  if (!LATTICE) return launch_grid_acq_v<KID, NI_MAX, LATTICE, 2, (NI_MAX <= 8 ? 4 : 3), 1>(p, T, st);
-  if (tiles == 2) return launch_grid_acq_v<KID, NI_MAX, LATTICE, 2, (NI_MAX <= 8 ? 3 : 2), 2>(p, T, st);
-  return launch_grid_acq_v<KID, NI_MAX, LATTICE, 2, (NI_MAX <= 8 ? 4 : 3), 1>(p, T, st);
+  return launch_grid_acq_v<KID, NI_MAX, false, 2, (NI_MAX <= 8 ? 4 : 3), 1>(p, T, st);
 }
 
-template <int KID, bool LATTICE>
+template <int KID>
 static int dispatch_ni(const GridAcqParams& p, int T, cudaStream_t st) {
-  if (p.n_cap <= 32) return launch_grid_acq<KID, 4, LATTICE>(p, T, st);
-  if (p.n_cap <= 64) return launch_grid_acq<KID, 8, LATTICE>(p, T, st);
-  return launch_grid_acq<KID, 16, LATTICE>(p, T, st);
+  if (p.n_cap <= 32) return launch_grid_acq<KID, 4>(p, T, st);
+  if (p.n_cap <= 64) return launch_grid_acq<KID, 8>(p, T, st);
+  return launch_grid_acq<KID, 16>(p, T, st);
 }
 
 // ktab[slot][dy * TW + dx] = s k(h sqrt(dx^2 + dy^2) / l): the same device function and the same
@@ -1121,14 +1118,13 @@ static int grid_acq_common(bool lattice, const double* grid, int G, int Gx, int 
   int rc;
   if (lattice) {
     // table look-ups do not depend on the kernel family: one set of instantiations serves all four
-    static const int legacy = env_int("B200BO_KB_LEGACY", 0);
-    rc = legacy ? dispatch_ni<B200BO_KERNEL_MATERN52, true>(p, T, st) : dispatch_lattice(p, T, st);
+    rc = dispatch_lattice(p, T, st);
   } else {
     switch (kernel_id) {
-      case B200BO_KERNEL_RBF: rc = dispatch_ni<B200BO_KERNEL_RBF, false>(p, T, st); break;
-      case B200BO_KERNEL_MATERN12: rc = dispatch_ni<B200BO_KERNEL_MATERN12, false>(p, T, st); break;
-      case B200BO_KERNEL_MATERN32: rc = dispatch_ni<B200BO_KERNEL_MATERN32, false>(p, T, st); break;
-      default: rc = dispatch_ni<B200BO_KERNEL_MATERN52, false>(p, T, st); break;
+      case B200BO_KERNEL_RBF: rc = dispatch_ni<B200BO_KERNEL_RBF>(p, T, st); break;
+      case B200BO_KERNEL_MATERN12: rc = dispatch_ni<B200BO_KERNEL_MATERN12>(p, T, st); break;
+      case B200BO_KERNEL_MATERN32: rc = dispatch_ni<B200BO_KERNEL_MATERN32>(p, T, st); break;
+      default: rc = dispatch_ni<B200BO_KERNEL_MATERN52>(p, T, st); break;
     }
   }
   if (rc) return rc;
