@@ -24,4 +24,5 @@ for tol in (0.1, -1.0):
         its = int(res.nit.sum())
         same = True if ref is None else bool(torch.equal(ref.picked, res.picked) and torch.equal(ref.yall, res.yall))
         if ref is None: ref = res
-        print("tol %5.1f groups %d: %.3f s, %d BO it, %.0f it/s, identical to one batch: %s" % (tol, groups, dt, its, its / dt, same), flush=True)
+        print("tol %5.1f groups %d: %.3f s, %d BO it, %.0f it/s, identical to one batch: %s, mean final gap %.4f" % (tol, groups, dt, its, its / dt, same, float((100.0 - res.yall[:, -1]).mean())), flush=True)
+
