@@ -145,7 +145,7 @@ struct GridAcqParams {
   const int32_t* ktab_id;   // (T) table slot per trial, or null = slot 0
 };
 
-template <int KID, int NI_MAX, bool LATTICE, int CH, int MINB, int NT>
+template <int KID, int NI_MAX, int CH, int MINB, int NT>
 __global__ void __launch_bounds__(GA_THREADS, MINB)
 grid_acq_kernel(const GridAcqParams p) {
   extern __shared__ __align__(16) double sm[];
@@ -171,7 +171,6 @@ grid_acq_kernel(const GridAcqParams p) {
   double* xs = sm + (size_t)nblk * 32;    // npad
   double* ys = xs + npad;
   double* al = ys + npad;
-  int* xyi = reinterpret_cast<int*>(al + npad);  // packed lattice coordinates x | y << 16 (LATTICE only)
   __shared__ double red_val[GA_WARPS];
   __shared__ int red_idx[GA_WARPS];
   __shared__ int red_flag;
@@ -185,17 +184,9 @@ grid_acq_kernel(const GridAcqParams p) {
       xs[j] = v ? p.X[((size_t)t * p.n_max + j) * 2] : 0.0;
       ys[j] = v ? p.X[((size_t)t * p.n_max + j) * 2 + 1] : 0.0;
       al[j] = v ? p.alpha[(size_t)t * p.n_max + j] : 0.0;
-      if (LATTICE) {
-        const double fx = rint((xs[j] - p.x0) / p.h), fy = rint((ys[j] - p.y0) / p.h);
-        const bool on = (p.x0 + p.h * fx == xs[j]) && (p.y0 + p.h * fy == ys[j]) && fx >= 0.0 && fy >= 0.0 &&
-                        fx < (double)p.Gx && fy < (double)p.Gy;
-        xyi[j] = on ? ((int)fx | ((int)fy << 16)) : 0;
-        if (v && !on && p.status) atomicOr(&p.status[t], B200BO_ST_OFF_LATTICE);
-      }
     }
     if (threadIdx.x == 0) red_flag = 0;
   }
-  const double* tab = LATTICE ? p.ktab + (size_t)(p.ktab_id ? p.ktab_id[t] : 0) * p.Gx * p.Gy : nullptr;
   const double cst = p.theta[(size_t)t * 4 + 1];
   const double sc = p.theta[(size_t)t * 4 + 2];
   const double ell = p.theta[(size_t)t * 4 + 3];
@@ -225,46 +216,20 @@ grid_acq_kernel(const GridAcqParams p) {
         const int gb = min(base + 8 * (q + tt) + bcol, p.G - 1);
         mu_part[tt] = 0.0;
         masked[tt] = 0;
-        if (LATTICE) {
-          const int gyi = gb / p.Gx, gxi = gb - gyi * p.Gx;
-          // chunks of 8 k-blocks: 8 index computations, then 8 independent table loads in flight,
-          // then 8 FMAs — one uniform branch per chunk instead of one per look-up
+        const double2 gp = __ldg(&p.grid[gb]);
 #pragma unroll
-          for (int Jb = 0; Jb < 2 * NI_MAX; Jb += 8) {
-            if (Jb < nJ) {
-              int kix[8];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const int j = 4 * (Jb + u) + jrow;
-                const int pk = xyi[j];
-                const int dxi = abs(gxi - (pk & 0xffff)), dyi = abs(gyi - (pk >> 16));
-                kix[u] = dyi * p.Gx + dxi;
-                masked[tt] |= (kix[u] == 0 && j < n) ? 1 : 0;     // dxi < Gx, so 0 <=> dxi == dyi == 0
-              }
-#pragma unroll
-              for (int u = 0; u < 8; ++u) kval[tt][Jb + u] = __ldg(tab + kix[u]);
-              // padded observations (j >= n) hit columns of L^-1 that are zero and alpha = 0: any finite
-              // table value is harmless there
-#pragma unroll
-              for (int u = 0; u < 8; ++u) mu_part[tt] = fma(kval[tt][Jb + u], al[4 * (Jb + u) + jrow], mu_part[tt]);
-            }
-          }
-        } else {
-          const double2 gp = __ldg(&p.grid[gb]);
-#pragma unroll
-          for (int J = 0; J < 2 * NI_MAX; ++J) {
-            kval[tt][J] = 0.0;
-            if (J < nJ) {
-              const int j = 4 * J + jrow;
-              const double dx = gp.x - xs[j], dy = gp.y - ys[j];
-              const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-              double kv = kernel_from_r2<KID>(r2, sc, ell, kp.a_scale);
-              const bool valid = j < n;
-              kv = valid ? kv : 0.0;
-              masked[tt] |= (valid && r2 == 0.0) ? 1 : 0;
-              kval[tt][J] = kv;
-              mu_part[tt] = fma(kv, al[j], mu_part[tt]);
-            }
+        for (int J = 0; J < 2 * NI_MAX; ++J) {
+          kval[tt][J] = 0.0;
+          if (J < nJ) {
+            const int j = 4 * J + jrow;
+            const double dx = gp.x - xs[j], dy = gp.y - ys[j];
+            const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            double kv = kernel_from_r2<KID>(r2, sc, ell, kp.a_scale);
+            const bool valid = j < n;
+            kv = valid ? kv : 0.0;
+            masked[tt] |= (valid && r2 == 0.0) ? 1 : 0;
+            kval[tt][J] = kv;
+            mu_part[tt] = fma(kv, al[j], mu_part[tt]);
           }
         }
       }
@@ -1012,20 +977,20 @@ inline int kb_ctas_per_sm(bool lattice, int n_cap) {
 
 inline size_t grid_acq_smem(int nI) {
   size_t npad = ((size_t)8 * nI + 31) & ~(size_t)31;
-  return ((size_t)nI * (nI + 1) * 32 + 3 * npad) * sizeof(double) + npad * sizeof(int);
+  return ((size_t)nI * (nI + 1) * 32 + 3 * npad) * sizeof(double);
 }
 
-template <int KID, int NI_MAX, bool LATTICE, int CH, int MINB, int NT>
+template <int KID, int NI_MAX, int CH, int MINB, int NT>
 static int launch_grid_acq_v(const GridAcqParams& p, int T, cudaStream_t st) {
   size_t smem = grid_acq_smem(NI_MAX);
-  cudaError_t e = cudaFuncSetAttribute(grid_acq_kernel<KID, NI_MAX, LATTICE, CH, MINB, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(grid_acq_kernel<KID, NI_MAX, CH, MINB, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e, "grid_posterior_acq_argmax: smem attribute");
   // dynamic smem sized by the largest n actually possible in this instantiation would waste
   // occupancy for small n; size it by n_max rounded to the tile instead.
   int nIa = (p.n_cap + 7) / 8;
   if (nIa > NI_MAX) nIa = NI_MAX;
   smem = grid_acq_smem(nIa);
-  grid_acq_kernel<KID, NI_MAX, LATTICE, CH, MINB, NT><<<(unsigned)((size_t)T * p.chunks), GA_THREADS, smem, st>>>(p);
+  grid_acq_kernel<KID, NI_MAX, CH, MINB, NT><<<(unsigned)((size_t)T * p.chunks), GA_THREADS, smem, st>>>(p);
   return 0;
 }
 
@@ -1037,7 +1002,7 @@ static int env_int(const char* name, int dflt) {
 // generic kernel: two accumulator chains per row-block group, one column tile per MMA group (measured best)
 template <int KID, int NI_MAX>
 static int launch_grid_acq(const GridAcqParams& p, int T, cudaStream_t st) {
-  return launch_grid_acq_v<KID, NI_MAX, false, 2, (NI_MAX <= 8 ? 4 : 3), 1>(p, T, st);
+  return launch_grid_acq_v<KID, NI_MAX, 2, (NI_MAX <= 8 ? 4 : 3), 1>(p, T, st);
 }
 
 template <int KID>
