@@ -35,6 +35,9 @@
 #ifndef KB8_RS_MAX_NI
 #define KB8_RS_MAX_NI 4      // byte-coordinate tile: reduce-scatter epilogue over four tiles up to this many row blocks
 #endif
+#ifndef KB8_MROW
+#define KB8_MROW 1           // byte-coordinate tile: posterior mean from a spare row of the last row block (MMA path)
+#endif
 #ifndef KB8_TAIL
 #define KB8_TAIL 1           // byte-coordinate tile: 1..2 live rows of the last row block by DFMA instead of DMMA
 #endif
@@ -540,12 +543,18 @@ grid_acq_lattice_kernel(const GridAcqParams p) {
 // 4-address broadcast LDS from the same fragment block), summed over the four k-row lanes at the end of the tile.
 // 2.75 cycles per (row, k-block) instead of 16 per k-block; the last k-block (columns >= 8 NI - 4 >= n) is not
 // needed at all. Rows r..TAIL-1 are zero in the fragment block and add nothing.
-template <int NI, bool EXACT, int TAIL>
+// MROW (only with EXACT, TAIL == 0, 3..7 live rows in the last row block): the posterior mean rides on the MMA path.
+// The kernel has written alpha into row 7 of the last row block of the STAGED copy of L^-1 (a spare row), so
+// C[7][col] of that block is sum_j alpha_j k*_j(col): the lanes with lane >> 2 == 7 end the tile holding the means of the
+// tile's eight candidates (returned in mu_part / mu_hi for columns 2 (lane & 3) and + 1) and the per-look-up DFMA and the
+// alpha loads disappear. Those lanes keep the spare row out of the sum of squares.
+template <int NI, bool EXACT, int TAIL, bool MROW = false>
 __device__ __forceinline__ void lattice_tile8(const double* __restrict__ wsm, const uint4* __restrict__ xyq,
                                               const double2* __restrict__ alq, const double* __restrict__ tab,
                                               unsigned wpk, unsigned cpk, int lane, int nI, double& ss0, double& ss1,
-                                              double& mu_part, double& tail_ss) {
+                                              double& mu_part, double& tail_ss, double* mu_hi = nullptr) {
   static_assert(TAIL == 0 || EXACT, "tail rows only for full-size trials");
+  static_assert(!MROW || (EXACT && TAIL == 0), "mean row only for full-size trials without tail rows");
   constexpr int ND = TAIL ? NI - 1 : NI;                   // row blocks on the MMA path
   constexpr int NJ = TAIL ? 2 * NI - 1 : 2 * NI;           // k-blocks that can hold a non-zero column
   double acc[ND > 0 ? ND : 1][2];
@@ -569,15 +578,22 @@ __device__ __forceinline__ void lattice_tile8(const double* __restrict__ wsm, co
       if ((J + 2) % 4 == 0) pq = xyq[(J + 2) / 4];
       kv1 = look_up((J + 2) % 4 == 0 ? pq.x : (J + 2) % 4 == 1 ? pq.y : (J + 2) % 4 == 2 ? pq.z : pq.w);
     }
-    if (J % 2 == 0) a2 = alq[J / 2];
-    // padded observations (j >= n) meet zero columns of L^-1 and alpha = 0: any finite value is harmless
-    mu_part = fma(kv, (J % 2 == 0) ? a2.x : a2.y, mu_part);
+    if (!MROW) {
+      if (J % 2 == 0) a2 = alq[J / 2];
+      // padded observations (j >= n) meet zero columns of L^-1 and alpha = 0: any finite value is harmless
+      mu_part = fma(kv, (J % 2 == 0) ? a2.x : a2.y, mu_part);
+    }
 #pragma unroll
     for (int I = J / 2; I < ND; ++I) {
       if (EXACT || I < nI) dmma_m8n8k4(acc[I][0], acc[I][1], wsm[(size_t)(I * (I + 1) + J) * 32 + lane], kv);
     }
 #pragma unroll
     for (int r = 0; r < TAIL; ++r) tl[r] = fma(wtail[J * 32 + 4 * r], kv, tl[r]);
+  }
+  if (MROW) {
+    mu_part = acc[ND - 1][0];
+    *mu_hi = acc[ND - 1][1];
+    if ((lane >> 2) == 7) { acc[ND - 1][0] = 0.0; acc[ND - 1][1] = 0.0; }
   }
   ss0 = 0.0;
   ss1 = 0.0;
@@ -690,6 +706,13 @@ grid_acq_lattice8_kernel(const GridAcqParams p) {
   // launch at n = 8k + 1, 8k + 2. Four DFMA rows (n = 8k + 3, 8k + 4) were measured too and LOSE 2..20 %: not built.
   static_assert(KB8_TAIL == 0 || KB8_TAIL == 1, "KB8_TAIL is a switch");
   const int tail_rows = (KB8_TAIL && nI == NI && n - 8 * (NI - 1) <= 2) ? 2 : 0;
+  // 3..7 live rows in the last row block: row 7 is spare and carries alpha (lattice_tile8, MROW); butterfly epilogue only
+  const bool mrow = KB8_MROW && NI > KB8_RS_MAX_NI && nI == NI && !tail_rows && n - 8 * (NI - 1) <= 7;
+  if (mrow) {                             // uniform
+    for (int j = threadIdx.x; j < 8 * NI; j += THREADS)
+      wsm[(size_t)((NI - 1) * NI + (j >> 2)) * 32 + 28 + (j & 3)] = alT[(j & 3) * ALS + (j >> 2)];
+    __syncthreads();
+  }
   const int j0 = lane & 1, j1 = (lane >> 1) & 1, b0 = (lane >> 2) & 1, b1 = (lane >> 3) & 1, b2 = lane >> 4;
 
   for (int base = col0 + warp * 32; base < col_end; base += NWARPS * 32) {
@@ -711,8 +734,9 @@ grid_acq_lattice8_kernel(const GridAcqParams p) {
 #pragma unroll 1
     for (int q = 0; q < 4; ++q) {
       const unsigned cpk = (unsigned)gxi | ((unsigned)gyi << 8);
-      double ss0, ss1, mp, tq;
+      double ss0, ss1, mp, tq, mh = 0.0;
       if (tail_rows == 2) lattice_tile8<NI, true, 2>(wsm, xyq, alq, tab, wpk, cpk, lane, nI, ss0, ss1, mp, tq);
+      else if (mrow) lattice_tile8<NI, true, 0, (NI > KB8_RS_MAX_NI)>(wsm, xyq, alq, tab, wpk, cpk, lane, nI, ss0, ss1, mp, tq, &mh);
       else if (nI == NI) lattice_tile8<NI, true, 0>(wsm, xyq, alq, tab, wpk, cpk, lane, nI, ss0, ss1, mp, tq);
       else lattice_tile8<NI, false, 0>(wsm, xyq, alq, tab, wpk, cpk, lane, nI, ss0, ss1, mp, tq);
       gxi += 8;
@@ -742,12 +766,19 @@ grid_acq_lattice8_kernel(const GridAcqParams p) {
           ss0 += __shfl_xor_sync(0xffffffffu, ss0, o);
           ss1 += __shfl_xor_sync(0xffffffffu, ss1, o);
         }
-#pragma unroll
-        for (int o = 1; o < 4; o <<= 1) mp += __shfl_xor_sync(0xffffffffu, mp, o);   // k-rows live in lane&3
         const int cc = lane & 7;                            // hand column cc of this tile to lane 8q + cc
+        double tm;
+        if (mrow) {                                         // uniform: the means sit complete on lanes 28..31
+          const double m0 = __shfl_sync(0xffffffffu, mp, 28 + (cc >> 1));
+          const double m1 = __shfl_sync(0xffffffffu, mh, 28 + (cc >> 1));
+          tm = (cc & 1) ? m1 : m0;
+        } else {
+#pragma unroll
+          for (int o = 1; o < 4; o <<= 1) mp += __shfl_xor_sync(0xffffffffu, mp, o);   // k-rows live in lane&3
+          tm = __shfl_sync(0xffffffffu, mp, cc * 4);
+        }
         const double t0 = __shfl_sync(0xffffffffu, ss0, cc >> 1);
         const double t1 = __shfl_sync(0xffffffffu, ss1, cc >> 1);
-        const double tm = __shfl_sync(0xffffffffu, mp, cc * 4);
         const double tt = tail_rows ? __shfl_sync(0xffffffffu, tq, cc * 4) : 0.0;
         if ((lane >> 3) == q) {
           ssF = ((cc & 1) ? t1 : t0) + tt;

@@ -249,9 +249,10 @@ def test_lattice_tiles_on_odd_shapes_equal_generic(shape):
 
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 9, 10, 11, 12, 13, 34, 44, 65, 68, 97, 100, 105, 121, 124])
 def test_lattice_tail_rows_off_the_mma_path(lattice_grid, n):
-    """Uniform batches whose last row block holds 1..2 live rows: the byte-coordinate tile takes those rows off the DMMA
-    path (per-lane DFMA chains), so var may differ from the generic kernel in the last bits — bounded here by 1e-13 s
-    (mu is computed identically); the pick must be the same unless the two best acquisition values tie to 1e-12."""
+    """Uniform batches with a ragged last row block. 1..2 live rows: the byte-coordinate tile takes them off the DMMA path
+    (per-lane DFMA chains), so var may differ from the generic kernel in the last bits (<= 1e-13 s). 3..7 live rows and
+    n > 32: alpha rides in the spare row 7 and the mean comes out of the MMAs, so mu differs in the last bits
+    (<= 1e-13 max|mu|). Otherwise bit-identical. The pick must be the same unless the two best values tie to 1e-12."""
     from b200bo import ops
     T = 4
     rng = np.random.default_rng(n)
@@ -271,11 +272,19 @@ def test_lattice_tail_rows_off_the_mma_path(lattice_grid, n):
     b = ops.grid_posterior_acq_argmax_lattice(lat, ktab, None, _to(X), st["wfrag"], st["alpha"], _to(nn), _to(th), _to(best), 3,
                                               debug=True)
     c = ops.grid_posterior_acq_argmax_lattice(lat, ktab, None, _to(X), st["wfrag"], st["alpha"], _to(nn), _to(th), _to(best), 3)
-    assert torch.equal(a["mu"], b["mu"]) and torch.equal(a["status"], b["status"])
+    assert torch.equal(a["status"], b["status"])
     s = th[0, 2]
+    live = (n - 1) % 8 + 1                               # live rows of the last row block
+    mean_on_mma = n > 32 and 3 <= live <= 7              # alpha rides in the spare row 7 (NI >= 5, no tail rows)
+    if mean_on_mma:                                      # mean summed in MMA order: last-bit differences only
+        assert float((a["mu"] - b["mu"]).abs().max()) <= 1e-13 * float(a["mu"].abs().max())
+    else:
+        assert torch.equal(a["mu"], b["mu"])
     assert float((a["var"] - b["var"]).abs().max()) <= 1e-13 * s
-    if (n - 1) % 8 >= 2:                                 # 3..8 live rows: everything stays on the MMA path
-        assert torch.equal(a["var"], b["var"]) and torch.equal(a["acq"], b["acq"])
+    if live >= 3:                                        # no tail rows: every row of V stays on the MMA path
+        assert torch.equal(a["var"], b["var"])
+        if not mean_on_mma:
+            assert torch.equal(a["acq"], b["acq"])
     for t in range(T):
         ia, ib, ic = int(a["idx"][t]), int(b["idx"][t]), int(c["idx"][t])
         acq = a["acq"][t]
