@@ -622,6 +622,96 @@ __host__ __device__ constexpr size_t lattice8_fixed_smem() {
   return (size_t)NI * (NI + 1) * 32 * sizeof(double) + 4 * (size_t)(lattice8_al_stride<NI>() + lattice8_xy_stride<NI>()) * 16;
 }
 
+// One super-tile = four column tiles = 32 candidates, for one tile variant (chosen once per CTA: the variant depends only
+// on the trial's n). Returns this lane's candidate offset `off` within the super-tile with its sum of squares and mean.
+//
+// Reduction of the four tiles' partial sums. NI <= KB8_RS_MAX_NI: a reduce-scatter — the shuffles share the LSU data
+// pipe with the fragment loads and the table gathers, and that pipe is 85-89 % busy at n <= 32 (ncu). A butterfly per
+// tile moves 44 words per tile through it; here every exchange halves the number of values a lane keeps (8 column
+// sums over the 8 row lanes: xor 4, 8, 16; 4 mean sums over the 4 k-row lanes: xor 1, 2), 22-24 words per FOUR tiles,
+// and each lane ends with exactly one candidate. The pairing order equals the butterfly's (same partner at every
+// level, fp add is commutative), so the sums are bit-identical to it. Measured: +4..13 % at n <= 24, nothing at
+// n = 32..48, -1 % from n = 64 on (the six values kept across tiles cost registers) — larger NI keep the per-tile butterfly.
+template <int NI, bool EXACT, int TAIL, bool MROW>
+__device__ __forceinline__ void lattice8_supertile(const double* __restrict__ wsm, const uint4* __restrict__ xyq,
+                                                   const double2* __restrict__ alq, const double* __restrict__ tab,
+                                                   unsigned wpk, int Gx, int Gy, int first, int lane, int nI,
+                                                   double& my_ss, double& my_mu, int& off) {
+  constexpr bool RS = NI <= KB8_RS_MAX_NI;
+  static_assert(!(RS && MROW), "the mean row is handed over by the butterfly epilogue only");
+  const int j0 = lane & 1, j1 = (lane >> 1) & 1, b0 = (lane >> 2) & 1, b1 = (lane >> 3) & 1, b2 = lane >> 4;
+  // lattice coordinates of this lane's candidate in tile 0 (first = base + lane / 4); later tiles step x by 8 (Gx >= 8).
+  // Candidates past G - 1 stay inside the table (their results are discarded by the caller).
+  int gyi = first / Gx, gxi = first - gyi * Gx;
+  gyi = min(gyi, Gy - 1);
+  double w_even = 0.0, m_even = 0.0, t_even = 0.0, u0 = 0.0, mu0 = 0.0, tt0 = 0.0;
+  double ssF = 0.0, muF = 0.0, ttF = 0.0;
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {
+    const unsigned cpk = (unsigned)gxi | ((unsigned)gyi << 8);
+    double ss0, ss1, mp, tq, mh = 0.0;
+    lattice_tile8<NI, EXACT, TAIL, MROW>(wsm, xyq, alq, tab, wpk, cpk, lane, nI, ss0, ss1, mp, tq, &mh);
+    gxi += 8;
+    if (gxi >= Gx) { gxi -= Gx; gyi = min(gyi + 1, Gy - 1); }
+    if constexpr (RS) {
+      // level 1 (row lanes xor 4): keep column 2 jrow + b0 of this tile
+      const double w = (b0 ? ss1 : ss0) + __shfl_xor_sync(0xffffffffu, b0 ? ss0 : ss1, 4);
+      if (!(q & 1)) {                                     // uniform
+        w_even = w; m_even = mp; t_even = tq;
+      } else {
+        // level 2 (xor 8): keep tile 2 (q / 2) + b1; mean level 1 (k-row lanes xor 1): keep tile 2 (q / 2) + j0
+        const double u = (b1 ? w : w_even) + __shfl_xor_sync(0xffffffffu, b1 ? w_even : w, 8);
+        const double mm = (j0 ? mp : m_even) + __shfl_xor_sync(0xffffffffu, j0 ? m_even : mp, 1);
+        const double tt = j0 ? tq : t_even;
+        if (q == 1) {
+          u0 = u; mu0 = mm; tt0 = tt;
+        } else {
+          // level 3 (xor 16): keep tile pair b2; mean level 2 (xor 2): keep tile pair j1
+          ssF = (b2 ? u : u0) + __shfl_xor_sync(0xffffffffu, b2 ? u0 : u, 16);
+          muF = (j1 ? mm : mu0) + __shfl_xor_sync(0xffffffffu, j1 ? mu0 : mm, 2);
+          ttF = j1 ? tt : tt0;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {                  // rows live in lane>>2
+        ss0 += __shfl_xor_sync(0xffffffffu, ss0, o);
+        ss1 += __shfl_xor_sync(0xffffffffu, ss1, o);
+      }
+      const int cc = lane & 7;                            // hand column cc of this tile to lane 8q + cc
+      double tm;
+      if constexpr (MROW) {                               // the means sit complete on lanes 28..31
+        const double m0 = __shfl_sync(0xffffffffu, mp, 28 + (cc >> 1));
+        const double m1 = __shfl_sync(0xffffffffu, mh, 28 + (cc >> 1));
+        tm = (cc & 1) ? m1 : m0;
+      } else {
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) mp += __shfl_xor_sync(0xffffffffu, mp, o);   // k-rows live in lane&3
+        tm = __shfl_sync(0xffffffffu, mp, cc * 4);
+      }
+      const double t0 = __shfl_sync(0xffffffffu, ss0, cc >> 1);
+      const double t1 = __shfl_sync(0xffffffffu, ss1, cc >> 1);
+      const double tt = TAIL ? __shfl_sync(0xffffffffu, tq, cc * 4) : 0.0;
+      if ((lane >> 3) == q) {
+        ssF = ((cc & 1) ? t1 : t0) + tt;
+        muF = tm;
+      }
+    }
+  }
+  if constexpr (RS) {
+    // this lane holds the column sum of candidate off = 8 (2 b2 + b1) + 4 j1 + 2 j0 + b0 of the super-tile; its mean (and
+    // tail sum) sit on the lane with column bits (j1, j0, b0) as row lane and tile bits (b2, b1) as k-row lane
+    const int src = 4 * (4 * j1 + 2 * j0 + b0) + 2 * b2 + b1;
+    my_mu = __shfl_sync(0xffffffffu, muF, src);
+    my_ss = ssF + (TAIL ? __shfl_sync(0xffffffffu, ttF, src) : 0.0);
+    off = 8 * (2 * b2 + b1) + 4 * j1 + 2 * j0 + b0;
+  } else {                                                // butterfly: lane l holds candidate l
+    my_mu = muF;
+    my_ss = ssF;
+    off = lane;
+  }
+}
+
 template <int NI, int THREADS>
 __global__ void __launch_bounds__(THREADS, (THREADS == 128 ? (NI <= 5 ? KB_MINB_SMALL : (NI <= 8 ? KB8_MINB_MID : 4)) : (THREADS == 256 ? 2 : 1)))
 grid_acq_lattice8_kernel(const GridAcqParams p) {
@@ -713,86 +803,17 @@ grid_acq_lattice8_kernel(const GridAcqParams p) {
       wsm[(size_t)((NI - 1) * NI + (j >> 2)) * 32 + 28 + (j & 3)] = alT[(j & 3) * ALS + (j >> 2)];
     __syncthreads();
   }
-  const int j0 = lane & 1, j1 = (lane >> 1) & 1, b0 = (lane >> 2) & 1, b1 = (lane >> 3) & 1, b2 = lane >> 4;
+  const int variant = tail_rows == 2 ? 0 : (mrow ? 1 : (nI == NI ? 2 : 3));     // tile variant of this trial
 
   for (int base = col0 + warp * 32; base < col_end; base += NWARPS * 32) {
-    // lattice coordinates of this lane's candidate in tile 0; later tiles step x by 8 (Gx >= 8). Candidates past
-    // G - 1 stay inside the table (their results are discarded below).
-    int gyi = (base + bcol) / p.Gx, gxi = (base + bcol) - gyi * p.Gx;
-    gyi = min(gyi, p.Gy - 1);
-    // Reduction of the four tiles' partial sums as a reduce-scatter: the shuffles share the LSU data pipe with the
-    // fragment loads and the table gathers, and that pipe is 85-89 % busy at n <= 32 (ncu). A butterfly per tile moves
-    // 44 words per tile through it; here every exchange halves the number of values a lane keeps (8 column sums over
-    // the 8 row lanes: xor 4, 8, 16; 4 mean sums over the 4 k-row lanes: xor 1, 2), 22-24 words per FOUR tiles, and
-    // each lane ends with exactly one candidate. The pairing order equals the butterfly's (same partner at every
-    // level, fp add is commutative), so the sums are bit-identical to it.
-    // (Measured: +4..13 % at n <= 24, nothing at n = 32..48, -1 % from n = 64 on, where the six values kept across
-    // tiles cost registers — so the reduce-scatter serves NI <= KB8_RS_MAX_NI and the per-tile butterfly the rest.)
-    constexpr bool RS = NI <= KB8_RS_MAX_NI;
-    double w_even = 0.0, m_even = 0.0, t_even = 0.0, u0 = 0.0, mu0 = 0.0, tt0 = 0.0;
-    double ssF = 0.0, muF = 0.0, ttF = 0.0;
-#pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
-      const unsigned cpk = (unsigned)gxi | ((unsigned)gyi << 8);
-      double ss0, ss1, mp, tq, mh = 0.0;
-      if (tail_rows == 2) lattice_tile8<NI, true, 2>(wsm, xyq, alq, tab, wpk, cpk, lane, nI, ss0, ss1, mp, tq);
-      else if (mrow) lattice_tile8<NI, true, 0, (NI > KB8_RS_MAX_NI)>(wsm, xyq, alq, tab, wpk, cpk, lane, nI, ss0, ss1, mp, tq, &mh);
-      else if (nI == NI) lattice_tile8<NI, true, 0>(wsm, xyq, alq, tab, wpk, cpk, lane, nI, ss0, ss1, mp, tq);
-      else lattice_tile8<NI, false, 0>(wsm, xyq, alq, tab, wpk, cpk, lane, nI, ss0, ss1, mp, tq);
-      gxi += 8;
-      if (gxi >= p.Gx) { gxi -= p.Gx; gyi = min(gyi + 1, p.Gy - 1); }
-      if constexpr (RS) {
-        // level 1 (row lanes xor 4): keep column 2 jrow + b0 of this tile
-        const double w = (b0 ? ss1 : ss0) + __shfl_xor_sync(0xffffffffu, b0 ? ss0 : ss1, 4);
-        if (!(q & 1)) {                                     // uniform
-          w_even = w; m_even = mp; t_even = tq;
-        } else {
-          // level 2 (xor 8): keep tile 2 (q / 2) + b1; mean level 1 (k-row lanes xor 1): keep tile 2 (q / 2) + j0
-          const double u = (b1 ? w : w_even) + __shfl_xor_sync(0xffffffffu, b1 ? w_even : w, 8);
-          const double mm = (j0 ? mp : m_even) + __shfl_xor_sync(0xffffffffu, j0 ? m_even : mp, 1);
-          const double tt = j0 ? tq : t_even;
-          if (q == 1) {
-            u0 = u; mu0 = mm; tt0 = tt;
-          } else {
-            // level 3 (xor 16): keep tile pair b2; mean level 2 (xor 2): keep tile pair j1
-            ssF = (b2 ? u : u0) + __shfl_xor_sync(0xffffffffu, b2 ? u0 : u, 16);
-            muF = (j1 ? mm : mu0) + __shfl_xor_sync(0xffffffffu, j1 ? mu0 : mm, 2);
-            ttF = j1 ? tt : tt0;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {                  // rows live in lane>>2
-          ss0 += __shfl_xor_sync(0xffffffffu, ss0, o);
-          ss1 += __shfl_xor_sync(0xffffffffu, ss1, o);
-        }
-        const int cc = lane & 7;                            // hand column cc of this tile to lane 8q + cc
-        double tm;
-        if (mrow) {                                         // uniform: the means sit complete on lanes 28..31
-          const double m0 = __shfl_sync(0xffffffffu, mp, 28 + (cc >> 1));
-          const double m1 = __shfl_sync(0xffffffffu, mh, 28 + (cc >> 1));
-          tm = (cc & 1) ? m1 : m0;
-        } else {
-#pragma unroll
-          for (int o = 1; o < 4; o <<= 1) mp += __shfl_xor_sync(0xffffffffu, mp, o);   // k-rows live in lane&3
-          tm = __shfl_sync(0xffffffffu, mp, cc * 4);
-        }
-        const double t0 = __shfl_sync(0xffffffffu, ss0, cc >> 1);
-        const double t1 = __shfl_sync(0xffffffffu, ss1, cc >> 1);
-        const double tt = tail_rows ? __shfl_sync(0xffffffffu, tq, cc * 4) : 0.0;
-        if ((lane >> 3) == q) {
-          ssF = ((cc & 1) ? t1 : t0) + tt;
-          muF = tm;
-        }
-      }
+    double my_ss, my_mu;
+    int off;
+    switch (variant) {                                    // uniform
+      case 0: lattice8_supertile<NI, true, 2, false>(wsm, xyq, alq, tab, wpk, p.Gx, p.Gy, base + bcol, lane, nI, my_ss, my_mu, off); break;
+      case 1: lattice8_supertile<NI, true, 0, (NI > KB8_RS_MAX_NI)>(wsm, xyq, alq, tab, wpk, p.Gx, p.Gy, base + bcol, lane, nI, my_ss, my_mu, off); break;
+      case 2: lattice8_supertile<NI, true, 0, false>(wsm, xyq, alq, tab, wpk, p.Gx, p.Gy, base + bcol, lane, nI, my_ss, my_mu, off); break;
+      default: lattice8_supertile<NI, false, 0, false>(wsm, xyq, alq, tab, wpk, p.Gx, p.Gy, base + bcol, lane, nI, my_ss, my_mu, off); break;
     }
-    // reduce-scatter: this lane holds the column sum of candidate off = 8 (2 b2 + b1) + 4 j1 + 2 j0 + b0 of the
-    // super-tile; its mean (and tail sum) sit on the lane with column bits (j1, j0, b0) as row lane and tile bits
-    // (b2, b1) as k-row lane. Butterfly: lane l holds candidate l.
-    const int src = 4 * (4 * j1 + 2 * j0 + b0) + 2 * b2 + b1;
-    const double my_mu = RS ? __shfl_sync(0xffffffffu, muF, src) : muF;
-    const double my_ss = RS ? ssF + (tail_rows ? __shfl_sync(0xffffffffu, ttF, src) : 0.0) : ssF;
-    const int off = RS ? 8 * (2 * b2 + b1) + 4 * j1 + 2 * j0 + b0 : lane;
     const int g = base + off;
     const bool my_masked = (obsbits[(base - col0) >> 5] >> off) & 1u;
     const double mu = cst + my_mu;
