@@ -152,6 +152,10 @@ int b200bo_gp_zvec(const double* y, const int32_t* n, const double* theta, const
  * Optional debug fields mu/var/acq (T,G) f64 (NULL to skip).
  * ws: >= b200bo_grid_acq_workspace_bytes(T, G). */
 size_t b200bo_grid_acq_workspace_bytes(int T, int G);
+/* Column chunks (CTAs) per trial a K-B launch of T trials over G candidates with at most n_cap observations will use
+ * (lattice != 0: the lattice entry). Host-only, no CUDA call: for tests and capacity planning. Never more than the
+ * workspace above is sized for. */
+int b200bo_grid_acq_chunks(int T, int G, int n_cap, int lattice);
 int b200bo_grid_posterior_acq_argmax(const double* grid, int G, const double* X, const double* wfrag,
                                      const double* alpha, const int32_t* n, const double* theta,
                                      const double* best_f, const uint8_t* extra_mask, int mask_observed,

@@ -35,6 +35,7 @@ PROTOTYPES = {
     "b200bo_gp_chol_append": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
     "b200bo_gp_zvec": (c_int, [P, P, P, P, P, c_int, c_int, P]),
     "b200bo_grid_acq_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "b200bo_grid_acq_chunks": (c_int, [c_int, c_int, c_int, c_int]),
     "b200bo_grid_posterior_acq_argmax": (c_int, [P, c_int, P, P, P, P, P, P, P, c_int, c_int, c_double, c_double,
                                                  P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, c_size_t, P]),
     "b200bo_kernel_table": (c_int, [P, c_int, c_int, c_double, c_int, c_int, P, P]),

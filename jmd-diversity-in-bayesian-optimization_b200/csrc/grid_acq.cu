@@ -1090,6 +1090,11 @@ size_t b200bo_grid_acq_workspace_bytes(int T, int G) {
   return (size_t)T * chunks * (sizeof(double) + sizeof(int32_t)) + 16;
 }
 
+int b200bo_grid_acq_chunks(int T, int G, int n_cap, int lattice) {
+  if (T <= 0 || G <= 0 || n_cap < 1) return 0;
+  return b200bo::pick_chunks(T, G, 148 * b200bo::kb_ctas_per_sm(lattice != 0, n_cap));
+}
+
 static int grid_acq_common(bool lattice, const double* grid, int G, int Gx, int Gy, double x0, double y0, double h,
                            const double* ktab, const int32_t* ktab_id, const double* X, const double* wfrag,
                            const double* alpha, const int32_t* n, const double* theta, const double* best_f,

@@ -22,6 +22,29 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.b200bo_wfrag_doubles(8) == 2 * 32 and lib.b200bo_wfrag_doubles(110) == 14 * 15 * 32
 
 
+def test_column_chunks_per_trial_fill_the_gpu_and_the_last_wave():
+    """K-B launches T x chunks CTAs (host rule b200bo::pick_chunks, no CUDA call): a single trial is split until the GPU
+    is full, a bench-size batch keeps one CTA per trial, a 1 000-trial batch takes a few chunks so that the last wave
+    of CTAs is not two-thirds empty; the workspace is sized for the largest choice."""
+    from b200bo import _lib
+    lib = _lib.load()
+    G = 10000
+    chunks = lib.b200bo_grid_acq_chunks
+    assert chunks(12500, G, 35, 1) == 1 and chunks(12500, G, 100, 1) == 1 and chunks(100000, G, 60, 1) == 1
+    assert chunks(1, G, 35, 1) == (G + 127) // 128                     # as many CTAs as 128-column chunks exist
+    c = chunks(1000, G, 35, 1)                                          # 740 resident CTAs: 1 000 CTAs = 2 waves for 1.35
+    assert 2 <= c <= 8
+    waves = lambda cc: -(-1000 * cc // 740) / cc
+    assert waves(c) < 0.8 * waves(1)
+    assert chunks(0, G, 35, 1) == 0 and chunks(5, 64, 10, 0) == 1       # empty batch; fewer candidates than one chunk
+    for T in (1, 7, 300, 1000, 5000, 12500):
+        for n_cap in (10, 64, 65, 128):
+            for lattice in (0, 1):
+                cc = chunks(T, G, n_cap, lattice)
+                assert 1 <= cc <= (G + 127) // 128
+                assert lib.b200bo_grid_acq_workspace_bytes(T, G) >= T * cc * 12
+
+
 def test_built_for_sm_100a_only():
     import subprocess
     from b200bo import _lib
