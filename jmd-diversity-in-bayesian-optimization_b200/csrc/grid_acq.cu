@@ -14,6 +14,17 @@
 // issued. Each lane evaluates the kernel for exactly the (j, column) pairs its B fragment
 // needs, so there is no redundancy and no shared-memory staging of k*.
 //
+// Three kernels share that mapping:
+//   grid_acq_kernel<KID, ...>            generic candidates: sqrt + exp per (observation, candidate) pair;
+//   grid_acq_lattice_kernel<NI, THREADS> candidates and observations on one lattice: kernel values from a table of
+//                                        lattice offsets (any lattice shape);
+//   grid_acq_lattice8_kernel<NI, THREADS> the production path for lattices with 8 <= Gx <= 255, Gy <= 256 (the
+//                                        reference's 100 x 100 and 200 x 200): byte-packed coordinates, 4-instruction
+//                                        look-ups, observed-point bit mask, EI survivors compacted per warp, ragged
+//                                        last row block (tail rows by DFMA / posterior mean in the spare row).
+// All three return the same arg-max; mu / var agree bit for bit except where the lattice8 comments say otherwise
+// (<= 1e-13 relative, tests/test_gpu_gp.py).
+//
 // Roofline: FP64 pipe (DMMA and DFMA share it on B200: tools/microbench/fp64_peaks.cu).
 // Algorithmic flops per (trial, launch): F_B(n, G) = G (n^2 + 17 n + 30);
 // algorithmic bytes: 24 n + 8 wfrag_doubles(n) + 40 read, 16 written per CTA + 16 G grid
