@@ -104,11 +104,14 @@ int b200bo_mt_seeded_randbelow(const int64_t* seeds, long long N, uint64_t n_lo,
  * surf (S,101,101) f32 out, row-major [iy][ix], max == 100. */
 int b200bo_wildcat_surface(const uint64_t* hseed, const int8_t* vecs, const double* peak_xy, const double* smooth,
                            const double* rug_amp, float* surf, int S, void* stream);
-/* objective evaluation f(x) of generate_cont() (Src/objectives.py:322-351, LinearNDInterpolator over the
- * 101x101 nodes): surf (S,101,101) f32, surf_id (M) int32 or NULL (surface 0), xy (M,2) f64 -> out (M) f64.
- * Node values are exact; inside a cell the main-diagonal triangulation is used; NaN outside [0,100]^2. */
-int b200bo_wildcat_eval(const float* surf, const int32_t* surf_id, const double* xy, double* out, long long M,
-                        void* stream);
+/* objective evaluation f(x) of generate_cont() (Src/objectives.py:322-351, scipy LinearNDInterpolator over the
+ * 101x101 nodes, :349-350): surf (S,101,101) f32, surf_id (M) int32 or NULL (surface 0), xy (M,2) f64 -> out (M) f64.
+ * diag_mask (100*100) uint8, [iy*100 + jx] = 1 when Qhull's Delaunay triangulation cuts cell
+ * [jx,jx+1]x[iy,iy+1] along (jx,iy)-(jx+1,iy+1), 0 along the other diagonal (exported once by
+ * tools/make_diag_mask.py — the split depends on the node coordinates only); NULL = main diagonal everywhere.
+ * Node values are exact, half-node values bit-identical to the interpolator's; NaN outside [0,100]^2. */
+int b200bo_wildcat_eval(const float* surf, const int32_t* surf_id, const uint8_t* diag_mask, const double* xy,
+                        double* out, long long M, void* stream);
 /* raw simplex noise at M points (M,2) f64 for one (hseed, vecs): SimpleNoise.py:85-172 */
 int b200bo_simplex_noise(uint64_t hseed, const int8_t* vecs_h, const double* xy, double* out, long long M,
                          void* stream);

@@ -218,16 +218,48 @@ def wildcat_surface(hseed: torch.Tensor, vecs: torch.Tensor, peak_xy: torch.Tens
     return surf
 
 
-def wildcat_eval(surf: torch.Tensor, xy: torch.Tensor, surf_id=None) -> torch.Tensor:
-    """f(x) for M points xy (M,2) f64 on surfaces surf (S,101,101) f32; surf_id (M,) int32 or None."""
+_DIAG_MASKS = {}
+
+
+def qhull_diag_mask(device) -> torch.Tensor:
+    """(10000,) uint8 on ``device``: the diagonal scipy's Delaunay (Qhull) triangulation cuts each unit cell of the
+    101 x 101 node lattice along (1 = main) — what LinearNDInterpolator in the reference's generate_cont()
+    (Src/objectives.py:349-350) interpolates on. Shipped as data/qhull_diag_101.bin (tools/make_diag_mask.py)."""
+    import os
+
+    import numpy as np
+    dev = torch.device(device)
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _DIAG_MASKS:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "qhull_diag_101.bin")
+        bits = np.unpackbits(np.fromfile(path, dtype=np.uint8))[:10000]
+        if bits.size != 10000:
+            raise _lib.B200boError(f"{path}: expected 10 000 cell bits")
+        _DIAG_MASKS[key] = torch.as_tensor(bits.copy(), dtype=torch.uint8, device=dev)
+    return _DIAG_MASKS[key]
+
+
+def wildcat_eval(surf: torch.Tensor, xy: torch.Tensor, surf_id=None, diag_mask="qhull") -> torch.Tensor:
+    """f(x) for M points xy (M,2) f64 on surfaces surf (S,101,101) f32; surf_id (M,) int32 or None.
+    diag_mask: "qhull" (default: the triangulation scipy builds for the reference), None (main diagonal in
+    every cell) or a (10000,) uint8 CUDA tensor."""
     lib = _lib.load()
     _cu(surf, torch.float32, "surf"); _cu(xy, torch.float64, "xy")
     if surf_id is not None:
         _cu(surf_id, torch.int32, "surf_id")
+    if isinstance(diag_mask, str):
+        if diag_mask != "qhull":
+            raise ValueError(f"diag_mask={diag_mask!r}")
+        diag_mask = qhull_diag_mask(xy.device)
+    if diag_mask is not None:
+        _cu(diag_mask, torch.uint8, "diag_mask")
+        if diag_mask.numel() != 10000:
+            raise _lib.B200boError("diag_mask: expected 100 x 100 cells")
     M = xy.shape[0]
     out = torch.empty(M, dtype=torch.float64, device=xy.device)
     if M:
-        check(lib.b200bo_wildcat_eval(_ptr(surf), _ptr(surf_id), _ptr(xy), _ptr(out), M, _stream()), "wildcat_eval")
+        check(lib.b200bo_wildcat_eval(_ptr(surf), _ptr(surf_id), _ptr(diag_mask), _ptr(xy), _ptr(out), M, _stream()),
+              "wildcat_eval")
     return out
 
 

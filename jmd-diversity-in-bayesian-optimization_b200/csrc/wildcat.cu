@@ -166,13 +166,19 @@ simplex_noise_kernel(unsigned long long hseed, double v0x, double v0y, double v1
   }
 }
 
-// Piecewise-linear evaluation of a surface between lattice nodes. At nodes the value is the fp32 node
-// value exactly, as the reference's LinearNDInterpolator gives (objectives.py:349-350; SURVEY.md
-// Appendix C). Inside a unit cell Qhull's Delaunay split is arbitrary (both diagonals are valid for a
-// square); this engine fixes the main diagonal (0,0)-(1,1) — a documented own convention.
-// Outside [0,100]^2: NaN, as the interpolator's fill value.
+// Piecewise-linear evaluation of a surface between lattice nodes = the LinearNDInterpolator that the
+// reference's generate_cont() returns (objectives.py:349-350). At nodes the value is the fp32 node value
+// exactly. Inside a unit cell the interpolant is linear on each of the two triangles of scipy's Delaunay
+// (Qhull) triangulation of the 101 x 101 nodes; which diagonal Qhull cuts a cell along depends on the node
+// coordinates only, so it is an input: diag_mask[iy*100 + jx] = 1 -> (jx,iy)-(jx+1,iy+1) ("main"),
+// 0 -> (jx+1,iy)-(jx,iy+1) ("anti"); NULL = main everywhere. The value is the barycentric sum
+// c0*v0 + c1*v1 + c2*v2 as scipy forms it (interpnd.pyx: _barycentric_coordinates + the weighted sum); with the
+// weights of a unit right triangle being exact differences of the fractional coordinates, half-node queries
+// (the 200 x 200 lattice of configs[3]) come out bit-identical, general queries within a few ulp.
+// Outside [0,100]^2: NaN, the interpolator's fill value.
 __global__ void __launch_bounds__(256)
-wildcat_eval_kernel(const float* __restrict__ surf, const int32_t* __restrict__ surf_id, const double2* __restrict__ xy,
+wildcat_eval_kernel(const float* __restrict__ surf, const int32_t* __restrict__ surf_id,
+                    const uint8_t* __restrict__ diag_mask, const double2* __restrict__ xy,
                     double* __restrict__ out, long long M) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x) {
     const double2 p = xy[i];
@@ -187,9 +193,16 @@ wildcat_eval_kernel(const float* __restrict__ surf, const int32_t* __restrict__ 
       const double u = p.x - jx, v = p.y - iy;
       const double v00 = s[iy * WW_SIDE + jx], v10 = s[iy * WW_SIDE + jx + 1];
       const double v01 = s[(iy + 1) * WW_SIDE + jx], v11 = s[(iy + 1) * WW_SIDE + jx + 1];
-      if (u == 0.0 && v == 0.0) r = v00;
-      else if (u >= v) r = v00 + u * (v10 - v00) + v * (v11 - v10);
-      else r = v00 + v * (v01 - v00) + u * (v11 - v01);
+      const bool main_diag = diag_mask ? (diag_mask[iy * (WW_SIDE - 1) + jx] != 0) : true;
+      double c0, c1, c2, a0, a1, a2;
+      if (main_diag) {
+        if (u >= v) { c0 = 1.0 - u; c1 = u - v; c2 = v; a0 = v00; a1 = v10; a2 = v11; }
+        else        { c0 = 1.0 - v; c1 = v - u; c2 = u; a0 = v00; a1 = v01; a2 = v11; }
+      } else {
+        if (u + v <= 1.0) { c0 = (1.0 - u) - v; c1 = u; c2 = v; a0 = v00; a1 = v10; a2 = v01; }
+        else              { c0 = (u - 1.0) + v; c1 = 1.0 - u; c2 = 1.0 - v; a0 = v11; a1 = v01; a2 = v10; }
+      }
+      r = __dadd_rn(__dadd_rn(__dmul_rn(c0, a0), __dmul_rn(c1, a1)), __dmul_rn(c2, a2));
     }
     out[i] = r;
   }
@@ -199,14 +212,16 @@ wildcat_eval_kernel(const float* __restrict__ surf, const int32_t* __restrict__ 
 
 extern "C" {
 
-int b200bo_wildcat_eval(const float* surf, const int32_t* surf_id, const double* xy, double* out, long long M, void* stream) {
+int b200bo_wildcat_eval(const float* surf, const int32_t* surf_id, const uint8_t* diag_mask, const double* xy, double* out,
+                        long long M, void* stream) {
   using namespace b200bo;
   if (M < 0) return arg_error("wildcat_eval: M=%lld", M);
   if (M == 0) return 0;
   if (!surf || !xy || !out) return arg_error("wildcat_eval: null pointer");
   long long blocks = (M + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  wildcat_eval_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(surf, surf_id, reinterpret_cast<const double2*>(xy), out, M);
+  wildcat_eval_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(surf, surf_id, diag_mask,
+                                                                      reinterpret_cast<const double2*>(xy), out, M);
   B200BO_CHECK_LAUNCH("wildcat_eval");
   return 0;
 }

@@ -17,9 +17,10 @@ from b200bo import host, ops
 
 
 class WildcatFunction:
-    """Callable f(x) over one surface: exact node values, piecewise-linear inside cells (main-diagonal
-    triangulation), NaN outside [0,100]^2 — the role of the scipy LinearNDInterpolator the reference
-    returns (objectives.py:349-350). Accepts numpy arrays, lists or torch tensors of shape (m,2) / (2,)."""
+    """Callable f(x) over one surface: exact node values, piecewise-linear on the triangles of scipy's Delaunay
+    (Qhull) triangulation of the 101 x 101 nodes (per-cell diagonal from ops.qhull_diag_mask), NaN outside
+    [0,100]^2 — the scipy LinearNDInterpolator the reference returns (objectives.py:349-350), bit-identical on
+    half-node queries. Accepts numpy arrays, lists or torch tensors of shape (m,2) / (2,)."""
 
     def __init__(self, X, surf, device=None):
         self.X = X

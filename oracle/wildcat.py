@@ -238,3 +238,48 @@ def lattice_lookup(surf: np.ndarray, xy: np.ndarray) -> np.ndarray:
     if not (np.all(ix == xy[..., 0]) and np.all(iy == xy[..., 1])):
         raise ValueError("lattice_lookup only defined on lattice nodes")
     return surf[iy, ix]
+
+
+def diag_mask_from_triangulation(points: np.ndarray, simplices: np.ndarray) -> np.ndarray:
+    """(100,100) uint8 from the Delaunay triangulation held by the reference's interpolator
+    (``generate_cont().tri``, objectives.py:349-350): 1 where cell [jx,jx+1]x[iy,iy+1] is cut along
+    (jx,iy)-(jx+1,iy+1), 0 along the other diagonal."""
+    p = np.asarray(points)[np.asarray(simplices)]
+    lo = p.min(axis=1)
+    if not np.all(p.max(axis=1) - lo == 1):
+        raise ValueError("not a triangulation of the unit lattice")
+    has00 = np.any(np.all(p == lo[:, None, :], axis=2), axis=1)
+    has11 = np.any(np.all(p == lo[:, None, :] + 1, axis=2), axis=1)
+    mask = np.zeros((100, 100), dtype=np.uint8)
+    seen = np.zeros((100, 100), dtype=np.int32)
+    jx, iy = lo[:, 0].astype(int), lo[:, 1].astype(int)
+    np.add.at(mask, (iy, jx), (has00 & has11).astype(np.uint8))
+    np.add.at(seen, (iy, jx), 1)
+    if not (np.all(seen == 2) and np.all((mask == 0) | (mask == 2))):
+        raise ValueError("every cell must consist of two triangles sharing one diagonal")
+    return (mask // 2).astype(np.uint8)
+
+
+def interp_linear(surf: np.ndarray, xy: np.ndarray, diag_mask=None) -> np.ndarray:
+    """``generate_cont()(xy)`` (objectives.py:322-351): scipy LinearNDInterpolator over the 101 x 101 nodes,
+    restated — find the unit cell, pick the triangle of the Delaunay split (``diag_mask`` (100,100), 1 = main
+    diagonal; None = main everywhere), value = sum of barycentric weight x node value (scipy interpnd.pyx);
+    NaN outside [0,100]^2. ``xy[:,0]`` is x (column), ``xy[:,1]`` y (row)."""
+    xy = np.asarray(xy, dtype=np.float64).reshape(-1, 2)
+    s = np.asarray(surf, dtype=np.float64)
+    x, y = xy[:, 0], xy[:, 1]
+    inside = (x >= 0) & (x <= 100) & (y >= 0) & (y <= 100)
+    xs, ys = np.where(inside, x, 0.0), np.where(inside, y, 0.0)
+    jx = np.minimum(np.floor(xs).astype(np.int64), 99)
+    iy = np.minimum(np.floor(ys).astype(np.int64), 99)
+    u, v = xs - jx, ys - iy
+    v00, v10, v01, v11 = s[iy, jx], s[iy, jx + 1], s[iy + 1, jx], s[iy + 1, jx + 1]
+    main = np.ones(len(x), dtype=bool) if diag_mask is None else (np.asarray(diag_mask).reshape(100, 100)[iy, jx] != 0)
+    lower = u >= v
+    below = u + v <= 1.0
+    out = np.where(main,
+                   np.where(lower, (1.0 - u) * v00 + (u - v) * v10 + v * v11,
+                            (1.0 - v) * v00 + (v - u) * v01 + u * v11),
+                   np.where(below, ((1.0 - u) - v) * v00 + u * v10 + v * v01,
+                            ((u - 1.0) + v) * v11 + (1.0 - u) * v01 + (1.0 - v) * v10))
+    return np.where(inside, out, np.nan)

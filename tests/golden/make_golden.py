@@ -76,6 +76,44 @@ def gen_wildcat():
     np.savez_compressed(os.path.join(HERE, "wildcat.npz"), **out)
 
 
+def gen_wildcat_cont():
+    """generate_cont() (objectives.py:322-351) off the nodes: the reference's own LinearNDInterpolator on the
+    200 x 200 half-node lattice of configs[3] (data_gen.constructX(budget=40000)), on random queries, on the
+    hull boundary / outside it, plus the Delaunay split its triangulation uses (per-cell diagonal)."""
+    from oracle import wildcat as owc
+    ob = refshim.load("objectives")
+    dg = refshim.load("data_gen")
+    d = dg.diverse_data_generator()
+    d.options["bounds"] = [(0, 100), (0, 100)]
+    d.constructX(budget=40000)
+    out = {"lattice200": np.asarray(d.X, dtype=np.float64)}
+    cases = [(0, 0.2, 0.2), (3, 0.8, 0.4)]
+    out["cases"] = np.array(cases)
+    rng = np.random.default_rng(99)
+    q = np.concatenate([rng.uniform(0, 100, size=(3000, 2)),
+                        np.stack([rng.integers(0, 100, 400) + 0.5, rng.integers(0, 100, 400) + 0.5], axis=1),   # cell centres
+                        np.stack([rng.integers(0, 101, 200).astype(float), rng.uniform(0, 100, 200)], axis=1),  # on cell edges
+                        rng.integers(0, 400, size=(400, 2)) / 4.0,                                              # quarter nodes
+                        np.array([[0, 0], [100, 100], [100, 0], [0, 100], [99.5, 0.5], [10.5, 20.25], [100, 37.25],
+                                  [-0.25, 5], [5, 100.5], [101, 101], [50, -1e-9]])])
+    out["queries"] = q
+    for i, (seed, sm, ra) in enumerate(cases):
+        o = ob.objectives()
+        o.bounds = [(0, 100), (0, 100)]
+        o.seed = seed
+        o.args = {"N": 1, "Smoothness": sm, "rug_freq": 1, "rug_amp": ra}
+        with quiet():
+            f = o.generate_cont()
+        out[f"lattice200_v_{i}"] = np.asarray(f(out["lattice200"]), dtype=np.float64)
+        out[f"queries_v_{i}"] = np.asarray(f(q), dtype=np.float64)
+        mask = owc.diag_mask_from_triangulation(f.tri.points, f.tri.simplices)
+        if i == 0:
+            out["diag_mask"] = mask
+        else:
+            assert np.array_equal(mask, out["diag_mask"]), "the Delaunay split must not depend on the surface"
+    np.savez_compressed(os.path.join(HERE, "wildcat_cont.npz"), **out)
+
+
 def gen_combinadics():
     cb = refshim.load("Combination")
     cf = cb.combination_finder()
@@ -242,6 +280,7 @@ def gen_hp_extract():
 if __name__ == "__main__":
     gen_simplex()
     gen_wildcat()
+    gen_wildcat_cont()
     gen_combinadics()
     gen_dpp()
     gen_author_data()

@@ -66,3 +66,35 @@ def test_many_surfaces_vs_oracle():
         ulp = np.spacing(np.abs(ref).astype(np.float32))
         assert np.all(np.abs(got[i] - ref) <= ulp)
         assert np.mean(got[i] == ref) > 0.999
+
+
+def test_generate_cont_off_node_matches_reference_interpolator(golden):
+    """b200bo_wildcat_eval with the Qhull diagonal mask vs the reference's generate_cont() outputs
+    (objectives.py:349-350): bit-identical on the whole 200 x 200 lattice of configs[3] (constructX(budget=40000)),
+    <= 1e-12 on 4 000 arbitrary queries, NaN outside [0,100]^2; oracle restatement bit for bit on random queries."""
+    from b200bo import ops
+    dev = torch.device("cuda:0")
+    c, w = golden("wildcat_cont.npz"), golden("wildcat.npz")
+    assert np.array_equal(ops.qhull_diag_mask(dev).cpu().numpy().reshape(100, 100), c["diag_mask"])
+    cases = [tuple(x) for x in w["cases"]]
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+    for i in range(len(c["cases"])):
+        surf = w[f"surf_{cases.index(tuple(c['cases'][i]))}"]
+        sd = t(surf).reshape(1, 101, 101)
+        got = ops.wildcat_eval(sd, t(c["lattice200"])).cpu().numpy()
+        assert np.array_equal(got, c[f"lattice200_v_{i}"])
+        got, ref = ops.wildcat_eval(sd, t(c["queries"])).cpu().numpy(), c[f"queries_v_{i}"]
+        ok = ~np.isnan(ref)
+        assert np.array_equal(np.isnan(got), ~ok) and np.all(np.abs(got[ok] - ref[ok]) <= 1e-12)
+        assert np.array_equal(got[ok], owc.interp_linear(surf, c["queries"], c["diag_mask"])[ok])
+        # explicit mask argument and the no-mask convention (main diagonal everywhere)
+        assert torch.equal(ops.wildcat_eval(sd, t(c["queries"]), diag_mask=ops.qhull_diag_mask(dev)).nan_to_num(-1.0),
+                           t(got).nan_to_num(-1.0))
+        plain = ops.wildcat_eval(sd, t(c["queries"]), diag_mask=None).cpu().numpy()
+        assert np.array_equal(plain[ok], owc.interp_linear(surf, c["queries"], None)[ok])
+    # two surfaces in one launch through surf_id
+    both = t(np.stack([w[f"surf_{cases.index(tuple(x))}"] for x in c["cases"]]))
+    q = t(np.concatenate([c["lattice200"][:5000], c["lattice200"][:5000]]))
+    sid = torch.cat([torch.zeros(5000, dtype=torch.int32, device=dev), torch.ones(5000, dtype=torch.int32, device=dev)])
+    got = ops.wildcat_eval(both, q, sid).cpu().numpy()
+    assert np.array_equal(got, np.concatenate([c["lattice200_v_0"][:5000], c["lattice200_v_1"][:5000]]))

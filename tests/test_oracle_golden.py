@@ -51,6 +51,31 @@ def test_wildcat_surfaces_bit_exact(golden):
     assert owc.peak_location(0) == (54.88135039273247, 67.781653679623)
 
 
+def test_generate_cont_off_node_values(golden):
+    """objectives.py:349-350: the restated LinearNDInterpolator with the Delaunay split of the reference's own
+    triangulation — bit-identical on the 200 x 200 half-node lattice of configs[3], <= 1e-12 on arbitrary queries,
+    NaN outside the hull; and the mask the product ships is the mask of the reference's interpolator object."""
+    import os
+    c, w = golden("wildcat_cont.npz"), golden("wildcat.npz")
+    mask = c["diag_mask"]
+    assert mask.shape == (100, 100) and set(np.unique(mask)) == {0, 1}
+    shipped = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                           "jmd-diversity-in-bayesian-optimization_b200", "b200bo", "data", "qhull_diag_101.bin")
+    assert np.array_equal(np.unpackbits(np.fromfile(shipped, dtype=np.uint8))[:10000].reshape(100, 100), mask)
+    assert c["lattice200"].shape == (40000, 2) and c["lattice200"][1, 0] == 0.5
+    for i in range(len(c["cases"])):
+        surf = w[f"surf_{[tuple(x) for x in w['cases']].index(tuple(c['cases'][i]))}"]
+        assert np.array_equal(owc.interp_linear(surf, c["lattice200"], mask), c[f"lattice200_v_{i}"])
+        got, ref = owc.interp_linear(surf, c["queries"], mask), c[f"queries_v_{i}"]
+        assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.isnan(ref).sum() == 4
+        ok = ~np.isnan(ref)
+        assert np.all(np.abs(got[ok] - ref[ok]) <= 1e-12)
+        # the split matters: the all-main-diagonal convention of round 1 is off by > 0.4 objective units somewhere
+        assert np.nanmax(np.abs(owc.interp_linear(surf, c["queries"], None) - ref)) > 0.4
+    q = np.array([[10.5, 20.25]])
+    assert abs(owc.interp_linear(w["surf_0"], q, mask)[0] - w["cont_v"][0]) <= 1e-12      # 33.34358835 (SURVEY App. C)
+
+
 def test_unrank_matches_reference_find_elm(golden):
     for row in golden("combinadics.json"):
         assert odpp.unrank(row["n"], row["k"], int(row["m"])) == row["set"]
