@@ -275,6 +275,10 @@ int b200bo_bo_update(const double* grid, int G, const float* obj, const int32_t*
                      double* X, double* y, int32_t* n, double* best_f, double* yall, int32_t* picked, int32_t* nit,
                      int T, int n_max, int max_iter, int iter, double tol, double optimal_y, void* stream);
 int b200bo_bo_finalize(double* yall, const int32_t* nit, int32_t* n, int T, int max_iter, void* stream);
+/* observation counts for the hyper-parameter fit before acquisition `iter` (BOloop, Src/BO.py:176-189,252): live
+ * trials, plus the trials that stopped in iteration iter-1 — the reference refits after every append, the last one
+ * included, and records that model. n_fit (T) int32 out: |n| for those trials, 0 otherwise. */
+int b200bo_bo_fit_counts(const int32_t* n, const int32_t* nit, int32_t* n_fit, int T, int iter, void* stream);
 
 #ifdef __cplusplus
 }

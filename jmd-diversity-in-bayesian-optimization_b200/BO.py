@@ -101,17 +101,18 @@ def fit_gpytorch_model(mll, device="cuda:0"):
     m = mll.model
     dev = torch.device(device)
     n = m.train_x.shape[0]
-    X = m.train_x.to(dev).reshape(1, n, 2).contiguous()
-    y = m.train_obj.to(dev).reshape(1, n).contiguous()
-    nn = torch.tensor([n], dtype=torch.int32, device=dev)
-    if n >= fit.LARGE_N:          # Experiment3-2-1.py:63-72 fits 1 010 ... 1 209 points: blocked K-C (csrc/gp_fit_large.cu)
-        r = fit.fit_large(X, y, nn, m.kernel_id, raw0=tuple(m.raw()))
-        m.set_raw(r["raw"][0].cpu().numpy())
-        return mll
-    f = fit.LBFGSFitter(1, dev, raw0=tuple(m.raw()))
-    theta = torch.empty((1, 4), dtype=torch.float64, device=dev)
-    f.fit_into(X, y, nn, m.kernel_id, theta)
-    m.set_raw(f.raw[0].cpu().numpy())
+    with torch.cuda.device(dev):
+        X = m.train_x.to(dev).reshape(1, n, 2).contiguous()
+        y = m.train_obj.to(dev).reshape(1, n).contiguous()
+        nn = torch.tensor([n], dtype=torch.int32, device=dev)
+        if n >= fit.LARGE_N:      # Experiment3-2-1.py:63-72 fits 1 010 ... 1 209 points: blocked K-C (csrc/gp_fit_large.cu)
+            r = fit.fit_large(X, y, nn, m.kernel_id, raw0=tuple(m.raw()))
+            m.set_raw(r["raw"][0].cpu().numpy())
+            return mll
+        f = fit.LBFGSFitter(1, dev, raw0=tuple(m.raw()))
+        theta = torch.empty((1, 4), dtype=torch.float64, device=dev)
+        f.fit_into(X, y, nn, m.kernel_id, theta)
+        m.set_raw(f.raw[0].cpu().numpy())
     return mll
 
 
@@ -144,7 +145,11 @@ def optimize_acqf_and_get_observation(acq_func, train_x, obj_func, raw, bound, r
                                       device="cuda:0"):
     """Arg-max of the acquisition over the candidate lattice and the objective there (BO.py:72-105).
     ``raw`` / ``restarts`` (Sobol samples / L-BFGS restarts of optimize_acqf) have no meaning on a grid."""
-    dev = torch.device(device)
+    with torch.cuda.device(torch.device(device)):
+        return _optimize_acqf_on_lattice(acq_func, obj_func, bound, budget, torch.device(device))
+
+
+def _optimize_acqf_on_lattice(acq_func, obj_func, bound, budget, dev):
     m = acq_func.model
     lat = _lattice_for(bound, budget)
     n = m.train_x.shape[0]
@@ -179,14 +184,16 @@ def _pack_result(res, i, nt, max_iter, minstate, optimal_y, X_train, hp_names=No
     r.yopt = torch.tensor(float(yobs.max()), dtype=torch.float32)
     r.xopt = torch.from_numpy(Xall[yobs == yobs.max()].astype(np.float32))
     r.nit = nit
-    r.success = not bool(int(res.status[i]) & (ops.ST_CHOL_FAIL | ops.ST_ALL_MASKED))
+    r.success = not bool(int(res.status[i]) & (ops.ST_CHOL_FAIL | ops.ST_ALL_MASKED | ops.ST_OFF_LATTICE))
     r.status = int(res.status[i])
     r._opt = optimal_y
     r.minstate = minstate
     r.traindata = X_train
     if res.thetas is not None:
         series = results.hp_series()
-        th = res.thetas[i, :nit].cpu().numpy()
+        # the model fitted after append k is what the reference records at iteration k (BO.py:176-189,252):
+        # thetas[:, k] is the fit on n0+k observations, so iterations 1..nit -> rows 1..nit
+        th = res.thetas[i, 1:nit + 1].cpu().numpy()
         for row in th:
             h = results.hp_result()
             inv_sp = lambda v: v if v > 20.0 else float(np.log(np.expm1(v)))
@@ -215,7 +222,13 @@ def BOloop_batched(obj_tables, surf_id, init_X, init_y, max_iter, theta=None, gr
     results trial by trial; pays when theta is None and the per-iteration fit has a long tail: b200bo.engine.run_concurrent);
     "auto" = 3 groups for fitted batches of at least 384 trials, else 1.
     Returns b200bo.engine.BOResult (device tensors)."""
-    dev = torch.device(device)
+    with torch.cuda.device(torch.device(device)):
+        return _boloop_batched(obj_tables, surf_id, init_X, init_y, max_iter, theta, grid, acq, acq_param, tol, optimal_y,
+                               nu, covar, torch.device(device), lattice, theta_rest, posterior, groups)
+
+
+def _boloop_batched(obj_tables, surf_id, init_X, init_y, max_iter, theta, grid, acq, acq_param, tol, optimal_y, nu, covar,
+                    dev, lattice, theta_rest, posterior, groups):
     t = lambda a, dt: torch.as_tensor(a, dtype=dt).to(dev).contiguous()
     if grid is None:
         grid = ops.Lattice(100, 100)
@@ -253,7 +266,8 @@ def _single(obj_func, max_iter, X, Y, theta, bounds, tol, nu, covar, minstate, o
     train_x, train_obj, _ = generate_initial_data(X, Y, minstate, n=nt)
     dev = torch.device(device)
     lat = _lattice_for(bounds, budget)
-    table = _objective_table(obj_func, lat, dev)
+    with torch.cuda.device(dev):
+        table = _objective_table(obj_func, lat, dev)
     # minimisation = maximise -f (Optimizers.py:48-52): obj_func already is f_c there, Y = f_c(X)
     X0 = train_x.double().reshape(1, nt, 2)
     y0 = train_obj.double().reshape(1, nt)

@@ -63,6 +63,7 @@ PROTOTYPES = {
     "b200bo_bo_update": (c_int, [P, c_int, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_double,
                                  c_double, P]),
     "b200bo_bo_finalize": (c_int, [P, P, P, c_int, c_int, P]),
+    "b200bo_bo_fit_counts": (c_int, [P, P, P, c_int, c_int, P]),
 }
 
 _lib = None

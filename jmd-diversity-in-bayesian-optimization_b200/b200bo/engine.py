@@ -7,6 +7,7 @@ All state lives in HBM for the whole run; the host only enqueues launches.
 """
 from __future__ import annotations
 
+import functools
 from dataclasses import dataclass
 
 import torch
@@ -23,7 +24,19 @@ class BOResult:
     X: torch.Tensor         # (T, n_max, 2) f64 observations (initial set first)
     y: torch.Tensor         # (T, n_max) f64
     n: torch.Tensor         # (T,) int32 observations at the end
-    thetas: torch.Tensor | None = None   # (T, max_iter, 4) hyper-parameters used per iteration (fit mode)
+    thetas: torch.Tensor | None = None   # (T, max_iter+1, 4), fit mode: [:, k] = the fit on n0+k observations — used by
+    #                                       acquisition k (k < nit); [:, 1:nit+1] = what the reference records after every
+    #                                       append (res_hp.addhp, Src/BO.py:252)
+
+
+def _on_device(fn):
+    """Run a BatchedBO method with the batch's GPU as torch's current device: the C ABI launches on the current device
+    and ops._stream() hands it that device's current stream, whatever device the caller had selected."""
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+    return wrapper
 
 
 class BatchedBO:
@@ -31,12 +44,17 @@ class BatchedBO:
     which surface a trial optimises; X0 (T,n0,2) f64 and y0 (T,n0) f64 the initial sets; theta (T,4) or (4,)
     ACTUAL hyper-parameters held fixed, or None to refit before every acquisition (``fitter``)."""
 
-    def __init__(self, grid, obj, surf_id, X0, y0, max_iter, theta=None, kernel_id=ops.MATERN52, acq_id=ops.EI,
-                 acq_param=0.0, tol=0.1, optimal_y=100.0, var_floor=ops.VAR_FLOOR, fitter=None, check_every=8,
-                 lattice="auto", append=True, theta_rest=None, posterior="full"):
-        dev = grid.device
-        if dev.type != "cuda":
+    def __init__(self, grid, obj, surf_id, X0, y0, max_iter, **kwargs):
+        if grid.device.type != "cuda":
             raise ops._lib.B200boError("BatchedBO needs CUDA tensors: the engine has no CPU path")
+        self.device = grid.device
+        with torch.cuda.device(self.device):
+            self._setup(grid, obj, surf_id, X0, y0, max_iter, **kwargs)
+
+    def _setup(self, grid, obj, surf_id, X0, y0, max_iter, theta=None, kernel_id=ops.MATERN52, acq_id=ops.EI,
+               acq_param=0.0, tol=0.1, optimal_y=100.0, var_floor=ops.VAR_FLOOR, fitter=None, check_every=8,
+               lattice="auto", append=True, theta_rest=None, posterior="full"):
+        dev = grid.device
         self.grid = grid.contiguous()
         self.obj = obj.contiguous()
         self.T, self.n0 = y0.shape
@@ -91,6 +109,12 @@ class BatchedBO:
         # candidates on a regular lattice (data_gen.constructX) -> kernel values come from a table
         self.lattice = ops.Lattice.from_points(self.grid) if isinstance(lattice, str) and lattice == "auto" else lattice
         self.ktab = self.ktab_id = None
+        if self.lattice is not None and not bool(self.lattice.contains(self.X[:, :self.n0]).all()):
+            # an initial observation off the candidate lattice has no entry in the kernel table (the lattice kernels
+            # would only flag it, ST_OFF_LATTICE): such batches take the generic sqrt / exp kernel
+            if posterior == "incremental":
+                raise ops._lib.B200boError("initial observations are not nodes of the candidate lattice")
+            self.lattice = None
         if self.lattice is not None:
             if self.fixed:
                 uniq, inv = torch.unique(self.theta, dim=0, return_inverse=True)
@@ -116,10 +140,13 @@ class BatchedBO:
             uniq, _ = torch.unique(self.theta, dim=0, return_inverse=True)
             self.ktab2 = ops.kernel_table_signed(uniq.contiguous(), self.kernel_id, self.lattice)
             self.ws_inc = ops.grid_inc_workspace(T, G, dev)
-        self.thetas = None if self.fixed else torch.zeros((T, max(self.max_iter, 1), 4), dtype=f64, device=dev)
+        self.thetas = None if self.fixed else torch.zeros((T, self.max_iter + 1, 4), dtype=f64, device=dev)
+        self.n_fit = None if self.fixed else torch.zeros(T, dtype=i32, device=dev)
+        self.iters_done = 0
         self.launches = 0
         self.profile = None        # set to a list to collect (name, n, start_event, end_event) per launch
 
+    @_on_device
     def reset(self, X0, y0, surf_id=None):
         """Load a new batch of initial sets into the resident buffers (no allocation)."""
         self.X.zero_()
@@ -140,6 +167,7 @@ class BatchedBO:
             self.obs_mask.zero_()
             self.zvec.zero_()
         self.launches = 0
+        self.iters_done = 0
 
     def _timed(self, name, n, fn):
         if self.profile is None:
@@ -157,20 +185,27 @@ class BatchedBO:
             self.ktab = ops.kernel_table(uniq.contiguous(), self.kernel_id, self.lattice)
             self.ktab_id = inv.to(torch.int32).contiguous()
 
+    @_on_device
     def step(self, it: int):
         n_hint = self.n0 + it
         if self.theta_rest is not None and it == 1:
             self._switch_theta(self.theta_rest)
         if not self.fixed:
-            self._timed("fit", n_hint, lambda: self.fitter.fit_into(self.X, self.y, self.n, self.kernel_id, self.theta,
-                                                                    self.status, n_hint))
-            self.thetas[:, it] = self.theta
-            self.launches += self.fitter.last_launches
+            self._timed("fit", n_hint, lambda: self._fit(it, n_hint))
         self._timed("gp_chol", n_hint, lambda: self._factorise(it, n_hint))
         self._timed("grid_acq", n_hint, lambda: self._acquire(n_hint))
         ops.bo_update(self.grid, self.obj, self.surf_id, self.arg_idx, self.X, self.y, self.n, self.best_f, self.yall,
                       self.picked, self.nit, self.max_iter, it, self.tol, self.optimal_y)
         self.launches += 4
+
+    def _fit(self, it, n_hint):
+        """Hyper-parameter fit on the n0+it observations of every trial that ran iteration it-1: the live ones (their
+        theta drives acquisition ``it``) and the ones that just stopped (the reference refits and records after every
+        append, Src/BO.py:176-189,252)."""
+        ops.bo_fit_counts(self.n, self.nit, self.n_fit, it)
+        self.fitter.fit_into(self.X, self.y, self.n_fit, self.kernel_id, self.theta, self.status, n_hint)
+        self.thetas[:, it] = self.theta
+        self.launches += self.fitter.last_launches + 1
 
     def _factorise(self, it, n_hint):
         if not self.append or it == 0 or (it == 1 and self.theta_rest is not None):
@@ -203,6 +238,7 @@ class BatchedBO:
                                           status=self.status, ws=self.ws, arg_idx=self.arg_idx, arg_val=self.arg_val,
                                           n_hint=n_hint)
 
+    @_on_device
     def _inc_update(self, n_arr, first, acquire):
         ops.gp_chol_append(self.X, self.y, n_arr, self.theta, self.kernel_id, self.wfrag, self.zvec, self.alpha, None,
                            self.status, wrow_out=self.wrow)
@@ -224,6 +260,7 @@ class BatchedBO:
                       self.picked, self.nit, self.max_iter, it, self.tol, self.optimal_y)
         self.launches += 1
 
+    @_on_device
     def run_graphed(self) -> BOResult:
         """The whole run as ONE CUDA graph: the first call runs eagerly (warm-up: lazy module loads, attribute
         settings) and captures the launch sequence of every iteration (no host synchronisation exists inside when
@@ -245,22 +282,30 @@ class BatchedBO:
         self._graph.replay()
         return self._graph_result
 
+    @_on_device
     def _begin(self):
         ops.bo_init(self.y, self.n, self.best_f, self.yall, self.picked, self.nit, self.max_iter, self.tol, self.optimal_y)
         self.launches += 1
 
+    @_on_device
     def _advance(self, it: int):
         if self.incremental:
             self._step_incremental(it)
         else:
             self.step(it)
+        self.iters_done = it + 1
 
+    @_on_device
     def _end(self) -> BOResult:
+        if not self.fixed and self.iters_done > 0:
+            # the model re-created after the LAST append is fitted and recorded too (Src/BO.py:176-189,252)
+            self._timed("fit", self.n0 + self.iters_done, lambda: self._fit(self.iters_done, self.n0 + self.iters_done))
         ops.bo_finalize(self.yall, self.nit, self.n, self.max_iter)
         self.launches += 1
         return BOResult(self.yall, self.picked[:, :self.max_iter], self.nit, self.status, self.X, self.y, self.n,
                         self.thetas)
 
+    @_on_device
     def run(self) -> BOResult:
         self._begin()
         for it in range(self.max_iter):

@@ -41,6 +41,10 @@ class LBFGSFitter:
 
     def fit_into(self, X, y, n, kernel_id, theta_out, status=None, n_hint=0):
         """Fit every trial with n[t] > 0 from the default start; writes ACTUAL theta (T,4) into theta_out."""
+        with torch.cuda.device(X.device):
+            return self._fit_into(X, y, n, kernel_id, theta_out, status, n_hint)
+
+    def _fit_into(self, X, y, n, kernel_id, theta_out, status, n_hint):
         lib = _lib.load()
         p, s = ops._ptr, ops._stream()
         T = self.T
@@ -87,6 +91,11 @@ LARGE_N = 128          # observation counts above the in-register K-C kernels (B
 def mll_value_grad_large(X, y, n, raw, kernel_id, status=None):
     """K-C for n up to 4000 (csrc/gp_fit_large.cu): X (T,n_max,2), y (T,n_max), n (T) i32, raw (T,4) ->
     value (T), grad (T,4)."""
+    with torch.cuda.device(X.device):
+        return _mll_value_grad_large(X, y, n, raw, kernel_id, status)
+
+
+def _mll_value_grad_large(X, y, n, raw, kernel_id, status):
     lib = _lib.load()
     p, s = ops._ptr, ops._stream()
     T, n_max = y.shape
@@ -102,6 +111,11 @@ def fit_large(X, y, n, kernel_id, raw0=DEFAULT_RAW, gtol=1e-5, ftol=2.2204460492
               max_rounds=600, status=None):
     """Fit T large models (one CTA each) from ``raw0``; returns dict(theta, raw, mll, iters) of device tensors.
     The batched counterpart of Experiment3-2-1.py's HPextract fan-out (one fit per ipyparallel engine there)."""
+    with torch.cuda.device(X.device):
+        return _fit_large(X, y, n, kernel_id, raw0, gtol, ftol, max_iter, max_ls, max_rounds, status)
+
+
+def _fit_large(X, y, n, kernel_id, raw0, gtol, ftol, max_iter, max_ls, max_rounds, status):
     lib = _lib.load()
     p, s = ops._ptr, ops._stream()
     dev = X.device

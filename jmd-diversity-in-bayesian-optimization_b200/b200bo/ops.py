@@ -22,6 +22,9 @@ VAR_FLOOR = 1e-9          # botorch 0.8.0 analytic EI clamp
 def _cu(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise _lib.B200boError(f"{name}: expected a CUDA tensor (the engine has no CPU path)")
+    if t.device.index != torch.cuda.current_device():
+        raise _lib.B200boError(f"{name}: tensor lives on {t.device} but the current device is cuda:{torch.cuda.current_device()} "
+                               "(the C ABI launches on the current device: wrap the call in torch.cuda.device(...))")
     if t.dtype != dtype:
         raise _lib.B200boError(f"{name}: expected dtype {dtype}, got {t.dtype}")
     if not t.is_contiguous():
@@ -455,6 +458,14 @@ class Lattice:
         iy = torch.arange(self.Gy, dtype=torch.float64, device=device) * self.h + self.y0
         return torch.stack([ix.repeat(self.Gy), iy.repeat_interleave(self.Gx)], dim=1).contiguous()
 
+    def contains(self, X: torch.Tensor) -> torch.Tensor:
+        """Per point of X (...,2): is it a node of this lattice? Same test as the kernels (csrc/grid_acq.cu staging:
+        x0 + h*rint((x-x0)/h) == x, unfused, index in range)."""
+        fx = torch.round((X[..., 0] - self.x0) / self.h)
+        fy = torch.round((X[..., 1] - self.y0) / self.h)
+        return ((self.x0 + self.h * fx == X[..., 0]) & (self.y0 + self.h * fy == X[..., 1]) & (fx >= 0) & (fy >= 0)
+                & (fx < self.Gx) & (fy < self.Gy))
+
     @staticmethod
     def from_points(grid):
         """Recognise a constructX-style lattice in a (G,2) point array (host-side, exact comparison)."""
@@ -551,6 +562,11 @@ def bo_finalize(yall, nit, n, max_iter):
     check(lib.b200bo_bo_finalize(_ptr(yall), _ptr(nit), _ptr(n), T, int(max_iter), _stream()), "bo_finalize")
 
 
+def bo_fit_counts(n, nit, n_fit, it):
+    lib = _lib.load()
+    check(lib.b200bo_bo_fit_counts(_ptr(n), _ptr(nit), _ptr(n_fit), n.numel(), int(it), _stream()), "bo_fit_counts")
+
+
 def bootstrap_ci(data: torch.Tensor, idx: torch.Tensor, percentiles=(2.5, 97.5)) -> torch.Tensor:
     """utils.bootstrap on device: data (N,C) f64, idx (B,N) int32 resampled rows -> (1 + len(percentiles), C) f64 =
     [mean over replicates, percentile...] of the replicate means (numpy summation order / "linear" percentiles)."""
@@ -567,3 +583,34 @@ def bootstrap_ci(data: torch.Tensor, idx: torch.Tensor, percentiles=(2.5, 97.5))
     check(_lib.load().b200bo_column_mean_percentiles(_ptr(boot), B, C, _ptr(q), len(percentiles), _ptr(out), _stream()),
           "column_mean_percentiles")
     return out
+
+
+# ------------------------------------------------------------------ device scoping
+# The C ABI launches on CUDA's *current* device and _stream() returns that device's current stream. Every public
+# wrapper above therefore runs with the device of its first CUDA tensor argument selected, so a caller that works on
+# cuda:N while another device is current (BO.py / Optimizers.py expose device='cuda:N') launches where its tensors live.
+
+def _device_scoped(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index == torch.cuda.current_device():
+                    return fn(*args, **kwargs)
+                with torch.cuda.device(a.device):
+                    return fn(*args, **kwargs)
+        for a in kwargs.values():
+            if isinstance(a, torch.Tensor) and a.is_cuda and a.device.index != torch.cuda.current_device():
+                with torch.cuda.device(a.device):
+                    return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+    return wrapper
+
+
+for _name, _fn in list(globals().items()):
+    if (callable(_fn) and not isinstance(_fn, type) and getattr(_fn, "__module__", None) == __name__
+            and not _name.startswith("_") and _name != "check"):
+        globals()[_name] = _device_scoped(_fn)
+del _name, _fn

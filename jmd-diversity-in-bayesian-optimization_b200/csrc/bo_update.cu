@@ -69,9 +69,31 @@ bo_finalize_kernel(double* __restrict__ yall, const int32_t* __restrict__ nit, i
   if (n[t] < 0) n[t] = -n[t];
 }
 
+// Which trials the hyper-parameter fit before acquisition `iter` covers: the live ones, plus the trials that stopped
+// in iteration iter-1 — the reference refits after EVERY append, also the last one, and records that model
+// (BO.py:176-189 then res_hp.addhp, :252), so a finished trial is fitted once more on its final data.
+__global__ void __launch_bounds__(128)
+bo_fit_counts_kernel(const int32_t* __restrict__ n, const int32_t* __restrict__ nit, int32_t* __restrict__ n_fit, int T,
+                     int iter) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  int nn = n[t];
+  n_fit[t] = nn > 0 ? nn : (nit[t] == iter && iter > 0 ? -nn : 0);
+}
+
 }  // namespace b200bo
 
 extern "C" {
+
+int b200bo_bo_fit_counts(const int32_t* n, const int32_t* nit, int32_t* n_fit, int T, int iter, void* stream) {
+  using namespace b200bo;
+  if (T < 0 || iter < 0) return arg_error("bo_fit_counts: bad sizes");
+  if (T == 0) return 0;
+  if (!n || !nit || !n_fit) return arg_error("bo_fit_counts: null pointer");
+  bo_fit_counts_kernel<<<(T + 127) / 128, 128, 0, as_stream(stream)>>>(n, nit, n_fit, T, iter);
+  B200BO_CHECK_LAUNCH("bo_fit_counts");
+  return 0;
+}
 
 int b200bo_bo_init(const double* y, int32_t* n, double* best_f, double* yall, int32_t* picked, int32_t* nit, int T,
                    int n_max, int max_iter, double tol, double optimal_y, void* stream) {

@@ -423,7 +423,7 @@ grid_acq_lattice_kernel(const GridAcqParams p) {
       const double y = v ? p.X[((size_t)t * p.n_max + j) * 2 + 1] : p.y0;
       al[j] = v ? p.alpha[(size_t)t * p.n_max + j] : 0.0;
       const double fx = rint((x - p.x0) / p.h), fy = rint((y - p.y0) / p.h);
-      const bool on = (p.x0 + p.h * fx == x) && (p.y0 + p.h * fy == y) && fx >= 0.0 && fy >= 0.0 &&
+      const bool on = (__dadd_rn(p.x0, __dmul_rn(p.h, fx)) == x) && (__dadd_rn(p.y0, __dmul_rn(p.h, fy)) == y) && fx >= 0.0 && fy >= 0.0 &&
                       fx < (double)p.Gx && fy < (double)p.Gy;
       xyi[j] = on ? ((int)fx | ((int)fy << 16)) : 0;
       if (v && !on && p.status) atomicOr(&p.status[t], B200BO_ST_OFF_LATTICE);
@@ -766,7 +766,7 @@ grid_acq_lattice8_kernel(const GridAcqParams p) {
       const double x = v ? p.X[((size_t)t * p.n_max + j) * 2] : p.x0;
       const double y = v ? p.X[((size_t)t * p.n_max + j) * 2 + 1] : p.y0;
       const double fx = rint((x - p.x0) / p.h), fy = rint((y - p.y0) / p.h);
-      const bool on = (p.x0 + p.h * fx == x) && (p.y0 + p.h * fy == y) && fx >= 0.0 && fy >= 0.0 &&
+      const bool on = (__dadd_rn(p.x0, __dmul_rn(p.h, fx)) == x) && (__dadd_rn(p.y0, __dmul_rn(p.h, fy)) == y) && fx >= 0.0 && fy >= 0.0 &&
                       fx < (double)p.Gx && fy < (double)p.Gy;
       const int xi = on ? (int)fx : 0, yi = on ? (int)fy : 0;
       xyT[(j & 3) * XYS + (j >> 2)] = (unsigned)xi | ((unsigned)yi << 8);

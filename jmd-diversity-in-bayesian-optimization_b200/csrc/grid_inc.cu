@@ -68,7 +68,7 @@ grid_inc_kernel(const GridIncParams p) {
   for (int j = threadIdx.x; j < n; j += GI_THREADS) {
     const double x = p.X[((size_t)t * p.n_max + j) * 2], y = p.X[((size_t)t * p.n_max + j) * 2 + 1];
     const double fx = rint((x - p.x0) / p.h), fy = rint((y - p.y0) / p.h);
-    const bool on = (p.x0 + p.h * fx == x) && (p.y0 + p.h * fy == y) && fx >= 0.0 && fy >= 0.0 &&
+    const bool on = (__dadd_rn(p.x0, __dmul_rn(p.h, fx)) == x) && (__dadd_rn(p.y0, __dmul_rn(p.h, fy)) == y) && fx >= 0.0 && fy >= 0.0 &&
                     fx < (double)p.Gx && fy < (double)p.Gy;
     const int xi = on ? (int)fx : 0, yi = on ? (int)fy : 0;
     ob[j] = (yi * W2 + xi - C0) * 8;                 // table BYTE offset = 8 (gy W2 + gx) - ob[j]

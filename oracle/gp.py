@@ -14,7 +14,7 @@ tests or golden vectors for it.  Anchors are the reference's call sites:
 * fit                      BO.py:144,189 (fit_gpytorch_model -> scipy L-BFGS-B)
 
 and the published formulas.  An independent check
-against scikit-learn's exact GP is in tests/test_oracle_gp.py.
+against scikit-learn's exact GP is in tests/test_oracle_golden.py.
 
 Conventions shared with the CUDA kernels (include/b200bo.h):
   theta = (noise sigma^2, constant c, outputscale s, lengthscale l)  — *actual* values
@@ -301,7 +301,8 @@ def bo_loop(grid, obj_values, X0, y0, max_iter, theta=None, kernel_id=MATERN52, 
 
     grid (G,2) f64 candidates; obj_values (G,) objective at each candidate
     (float32-representable, as ``torch.tensor(obj_func(new_x), dtype=float32)``, BO.py:104).
-    theta fixed for every iteration when given (the *intent* of BOloop_fixparam);
+    theta (4,) fixed for every iteration when given (the *intent* of BOloop_fixparam); theta (k,4): row i is used
+    by acquisition i (replay of recorded per-iteration fits);
     when None, ``fit(X, y, kernel_id) -> raw`` is called before every acquisition
     (BOloop: initial fit :144, refit from the default start after every append :176-189).
 
@@ -317,7 +318,12 @@ def bo_loop(grid, obj_values, X0, y0, max_iter, theta=None, kernel_id=MATERN52, 
     error = 100.0
     while error > tol and it < max_iter:
         it += 1
-        th = theta if theta is not None else raw_to_theta(fit(X, y, kernel_id))
+        if theta is None:
+            th = raw_to_theta(fit(X, y, kernel_id))
+        elif np.ndim(theta) == 2:
+            th = np.asarray(theta)[it - 1]          # replay: the hyper-parameters of acquisition it-1, given per iteration
+        else:
+            th = theta
         if theta_rest is not None and it > 1:
             th = theta_rest          # BOloop_fixparam as coded: defaults after the first re-created model (BO.py:424-429)
         thetas.append(np.array(th, dtype=np.float64))

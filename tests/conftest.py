@@ -58,3 +58,27 @@ def lattice_grid():
 AUTHOR_THETA_RAW = (0.0017619397258386016, 41.82688735961914, 190.43237411499024, 9.869425163269042)
 """(raw_noise, constant, raw_outputscale, raw_lengthscale): dominant KDE modes of the authors' fits for
 smoothness 0.2 / ruggedness 0.2 (tests/golden/author_hyperparams.json; BOloop_fixparam uses [0], BO.py:395)."""
+
+
+def verified_tie_mismatches(sets_sorted, dist_ref, raw_ref_sorted, gamma):
+    """Ranking parity with explicit tie accounting. ``sets_sorted`` (N,k,2) are our sets in rank order, ``dist_ref`` the
+    reference's, ``raw_ref_sorted`` the reference's raw log-det per rank. A rank b where the two differ is accepted only
+    if the set we placed there is the set the reference placed at some rank b' whose reference score is within the
+    conditioning bound of rank b's (oracle.dpp.cond_bound_rel of both sets: the reference's own LU is no closer to exact
+    arithmetic than that). Anything else raises. Returns the number of such verified swaps."""
+    from oracle import dpp as odpp
+    a = np.ascontiguousarray(np.asarray(sets_sorted).astype(np.int64))
+    r = np.ascontiguousarray(np.asarray(dist_ref).astype(np.int64))
+    same = np.all(a == r, axis=(1, 2))
+    bad = np.nonzero(~same)[0]
+    if len(bad) == 0:
+        return 0
+    where = {r[j].tobytes(): j for j in range(len(r))}
+    for b in bad:
+        bp = where.get(a[b].tobytes())
+        assert bp is not None, f"rank {b}: a set the reference's distribution does not contain"
+        bound = (odpp.cond_bound_rel(r[b].astype(np.float64), gamma) * abs(raw_ref_sorted[b])
+                 + odpp.cond_bound_rel(r[bp].astype(np.float64), gamma) * abs(raw_ref_sorted[bp]))
+        assert abs(raw_ref_sorted[bp] - raw_ref_sorted[b]) <= bound, \
+            f"rank {b} <-> {bp}: scores {raw_ref_sorted[b]!r} / {raw_ref_sorted[bp]!r} differ by more than the bound {bound:.3e}"
+    return len(bad)

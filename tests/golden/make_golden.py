@@ -186,6 +186,28 @@ def gen_dpp():
     np.savez_compressed(os.path.join(HERE, "dpp.npz"), **out)
 
 
+def gen_gammacalc():
+    """diverse_data_generator.gammacalc (data_gen.py:758-842): 16 x 16 rank-correlation matrix over gamma = 10^-12..10^3
+    (256 generate() calls of ``min_samples`` sets + a re-score each) and the widest correlated pair it returns, from the
+    reference's own code. np.random is seeded because gammacorrelation shuffles the order of a NaN batch (:773-774)."""
+    import warnings
+    dg = refshim.load("data_gen")
+    seed, min_samples, np_seed = 5, 60, 123
+    d = dg.diverse_data_generator()
+    d.options["bounds"] = [(0, 100), (0, 100)]
+    d.options["seed"] = seed
+    d.training_size = 10
+    np.random.seed(np_seed)
+    with warnings.catch_warnings(), quiet(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        pair = d.gammacalc(min_samples=min_samples)
+    grange = list(range(-12, 4))
+    matrix = [[float(d.gamma_correlation_dict[a][b]) for b in grange] for a in grange]
+    with open(os.path.join(HERE, "gammacalc.json"), "w") as fh:
+        json.dump({"seed": seed, "min_samples": min_samples, "np_seed": np_seed, "grange": grange, "matrix": matrix,
+                   "pair": [int(pair[0]), int(pair[1])]}, fh)
+
+
 def gen_author_data():
     """Fixed hyper-parameters the authors' runs used (BOloop_fixparam takes
     fixparam[name][0], BO.py:395).  Values read from
@@ -283,6 +305,7 @@ if __name__ == "__main__":
     gen_wildcat_cont()
     gen_combinadics()
     gen_dpp()
+    gen_gammacalc()
     gen_author_data()
     gen_bootstrap()
     gen_hp_extract()

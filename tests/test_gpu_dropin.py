@@ -82,7 +82,10 @@ def test_data_gen_generate_matches_reference(golden):
     assert np.all(np.diff(scores) >= 0)
     assert np.allclose(scores, g["gen_s0_scores"], rtol=0, atol=5e-5)        # z inherits conditioning-limited score error
     same = np.all(dist.astype(np.int16) == g["gen_s0_dist"], axis=(1, 2))
-    assert same.mean() > 0.998                                               # rank swaps only among near-ties
+    # rank swaps only between sets whose reference scores tie within the conditioning bound — each one verified
+    from conftest import verified_tie_mismatches
+    raw_ref_sorted = g["gen_s0_scores"] * sd_ref + mean_ref
+    assert verified_tie_mismatches(dist, g["gen_s0_dist"], raw_ref_sorted, 1e-5) <= 20
     s5 = d.sample(5)
     s95 = d.sample(95)
     assert list(d.acquiredsets) == list(g["gen_s0_acquired"])                # same ranks as the reference (462, 9409)

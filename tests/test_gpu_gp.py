@@ -293,6 +293,12 @@ def test_lattice_tail_rows_off_the_mma_path(lattice_grid, n):
             assert abs(float(acq[ia] - acq[ib])) <= 1e-12 * abs(float(acq[ia]))
         idx, val, sto, mu, var, aq = ogp.grid_step(lattice_grid, X[t], y[t], th[t], 3, return_fields=True)
         assert np.allclose(b["var"][t].cpu().numpy(), var, rtol=1e-8, atol=1e-10 * s)
+        assert np.allclose(a["var"][t].cpu().numpy(), var, rtol=1e-8, atol=1e-10 * s)
+        assert np.allclose(a["mu"][t].cpu().numpy(), mu, rtol=1e-8, atol=1e-8 * np.abs(mu).max())
+        # the arg-max of the production tail-row / mean-row variants is the ORACLE's arg-max; a different index is
+        # only acceptable on a rounding-level tie of the oracle's own acquisition values
+        assert ib == idx or abs(aq[ib] - aq[idx]) <= 1e-12 * abs(aq[idx]), (t, ib, idx)
+        assert ia == idx or abs(aq[ia] - aq[idx]) <= 1e-12 * abs(aq[idx]), (t, ia, idx)
 
 
 def test_lattice_half_step_grid_and_off_lattice_flag(golden):
