@@ -42,6 +42,8 @@ extern "C" {
 #define B200BO_ST_NONFINITE 4   /* NaN / +inf acquisition value seen                   */
 #define B200BO_ST_ALL_MASKED 8  /* no selectable candidate                             */
 #define B200BO_ST_OFF_LATTICE 16 /* lattice path given an off-lattice observation      */
+#define B200BO_ST_FALLBACK 32   /* b200bo_bo_fixed_loop handed the trial back untouched (non-positive pivot or
+                                   off-lattice start): run it through the per-iteration kernels */
 
 #define B200BO_NMAX 128         /* max observations per trial in the GP kernels        */
 
@@ -203,6 +205,32 @@ int b200bo_grid_posterior_update_acq_argmax(int Gx, int Gy, double x0, double y0
                                             int acq_id, double acq_param, double var_floor, int32_t* arg_idx,
                                             double* arg_val, double* acq, int32_t* status, int T, int n_max, void* ws,
                                             size_t ws_bytes, void* stream);
+
+/* ---- K-F  the whole fixed-hyper-parameter BO loop of a trial in one persistent CTA -----------------
+ * replaces BOloop_fixparam's loop body (Src/BO.py:404-446: ExpectedImprovement -> optimize_acqf -> objective ->
+ * torch.cat append -> yopt / yall.append -> re-created model with the same hyper-parameters) for ALL iterations of a
+ * trial: one launch instead of b200bo_gp_chol_append + b200bo_grid_posterior_update_acq_argmax + b200bo_bo_update per
+ * iteration. Same posterior recurrences as those entries (rank-1 row of L^-1, per-candidate (mu - c, s - var) folded
+ * row by row); the kernel table lives in shared memory, the per-candidate state in a per-CTA scratch (L2-resident).
+ * ktabY (H, 2Gy-1, Gx) f64 from b200bo_kernel_table_ysigned: ktabY[slot][(dy + Gy-1) Gx + |dx|]; ktab_id (T) or NULL;
+ * order (T) int32 processing order (e.g. trials sorted by slot, so a CTA reloads its table rarely) or NULL.
+ * In: X (T,n_max,2), y (T,n_max), n (T) = initial observations (>= 1). Out: X, y, n (observations at the end, positive),
+ * best_f (T), yall (T,max_iter+2) padded as BO.py:262-271, picked (T,max_iter) (-1 = none), nit (T), status (T).
+ * A trial whose start is off the lattice or whose appended pivot is not positive comes back with
+ * B200BO_ST_FALLBACK set, n = its initial count, nit = 0: the caller runs it through the per-iteration entries
+ * (psd_safe_cholesky's jitter rule lives in b200bo_gp_assemble_chol).
+ * b200bo_bo_fixed_loop_supported: does the lattice's table (+ n_max rows of L^-1) fit the 227 KB of shared memory
+ * (100 x 100 with n_max <= 116 does; 200 x 200 does not). ws: >= b200bo_bo_fixed_loop_workspace_bytes(T, Gx, Gy). */
+int b200bo_kernel_table_ysigned(const double* theta, int H, int kernel_id, double h, int Gx, int Gy, double* ktabY,
+                                void* stream);
+int b200bo_bo_fixed_loop_supported(int Gx, int Gy, int n_max);
+int b200bo_bo_fixed_loop_ctas(int T);
+size_t b200bo_bo_fixed_loop_workspace_bytes(int T, int Gx, int Gy);
+int b200bo_bo_fixed_loop(int Gx, int Gy, double x0, double y0, double h, const double* ktabY, const int32_t* ktab_id,
+                         const int32_t* order, const float* obj, const int32_t* surf_id, double* X, double* y, int32_t* n,
+                         const double* theta, double* best_f, double* yall, int32_t* picked, int32_t* nit,
+                         int32_t* status, int T, int n_max, int max_iter, int acq_id, double acq_param, double var_floor,
+                         double tol, double optimal_y, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- K-C  marginal log-likelihood value and gradient ----------------------------
  * replaces ExactMarginalLogLikelihood + autograd inside fit_gpytorch_model (BO.py:144,189).

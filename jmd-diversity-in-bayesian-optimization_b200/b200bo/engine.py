@@ -90,12 +90,33 @@ class BatchedBO:
             self.theta_first = self.theta.clone()
         self.kernel_id, self.acq_id, self.acq_param = int(kernel_id), int(acq_id), float(acq_param)
         self.tol, self.optimal_y, self.var_floor = float(tol), float(optimal_y), float(var_floor)
-        self.alpha = torch.zeros((T, n_max), dtype=f64, device=dev)
-        self.wfrag = torch.zeros((T, ops.wfrag_doubles(n_max)), dtype=f64, device=dev)
+        # candidates on a regular lattice (data_gen.constructX) -> kernel values come from a table
+        self.lattice = ops.Lattice.from_points(self.grid) if isinstance(lattice, str) and lattice == "auto" else lattice
+        if self.lattice is not None and not bool(self.lattice.contains(self.X[:, :self.n0]).all()):
+            # an initial observation off the candidate lattice has no entry in the kernel table (the lattice kernels
+            # would only flag it, ST_OFF_LATTICE): such batches take the generic sqrt / exp kernel
+            if posterior in ("incremental", "persistent"):
+                raise ops._lib.B200boError("initial observations are not nodes of the candidate lattice")
+            self.lattice = None
         # fixed theta: L^-1 grows by one row per iteration (rank-1 append) instead of being refactorised
         self.append = bool(append) and self.fixed
-        self.zvec = torch.zeros((T, n_max), dtype=f64, device=dev) if self.append else None
-        self.n_redo = torch.zeros(T, dtype=i32, device=dev) if self.append else None
+        # persistent: the whole loop of a trial in one CTA (csrc/bo_persist.cu) — fixed theta, lattice candidates whose
+        # kernel table fits shared memory; "auto" takes it whenever it applies, else the full recomputation
+        can_persist = (self.fixed and self.lattice is not None and self.append and theta_rest is None and self.max_iter > 0
+                       and ops.bo_fixed_loop_supported(self.lattice, n_max))
+        if posterior == "persistent" and not can_persist:
+            raise ops._lib.B200boError("posterior='persistent' needs fixed theta, append=True, no theta_rest and a candidate "
+                                       "lattice whose kernel table fits shared memory (100x100 with n0+max_iter <= 116)")
+        if posterior == "auto":
+            posterior = "persistent" if can_persist else "full"
+        self.persistent = posterior == "persistent"
+        self._kwargs = dict(kernel_id=kernel_id, acq_id=acq_id, acq_param=acq_param, tol=tol, optimal_y=optimal_y,
+                            var_floor=var_floor, check_every=check_every, append=append)
+        classic = not self.persistent                    # the per-iteration kernels' state (0.7 GB at T = 12 500)
+        self.alpha = torch.zeros((T, n_max), dtype=f64, device=dev) if classic else None
+        self.wfrag = torch.zeros((T, ops.wfrag_doubles(n_max)), dtype=f64, device=dev) if classic else None
+        self.zvec = torch.zeros((T, n_max), dtype=f64, device=dev) if self.append and classic else None
+        self.n_redo = torch.zeros(T, dtype=i32, device=dev) if self.append and classic else None
         self.best_f = torch.empty(T, dtype=f64, device=dev)
         self.yall = torch.zeros((T, self.max_iter + 2), dtype=f64, device=dev)
         self.picked = torch.empty((T, max(self.max_iter, 1)), dtype=i32, device=dev)
@@ -103,19 +124,19 @@ class BatchedBO:
         self.status = torch.zeros(T, dtype=i32, device=dev)
         self.arg_idx = torch.empty(T, dtype=i32, device=dev)
         self.arg_val = torch.empty(T, dtype=f64, device=dev)
-        self.ws = ops.grid_acq_workspace(T, self.G, dev)
+        self.ws = ops.grid_acq_workspace(T, self.G, dev) if classic else None
         self.check_every = int(check_every)
         self.posterior = posterior
-        # candidates on a regular lattice (data_gen.constructX) -> kernel values come from a table
-        self.lattice = ops.Lattice.from_points(self.grid) if isinstance(lattice, str) and lattice == "auto" else lattice
         self.ktab = self.ktab_id = None
-        if self.lattice is not None and not bool(self.lattice.contains(self.X[:, :self.n0]).all()):
-            # an initial observation off the candidate lattice has no entry in the kernel table (the lattice kernels
-            # would only flag it, ST_OFF_LATTICE): such batches take the generic sqrt / exp kernel
-            if posterior == "incremental":
-                raise ops._lib.B200boError("initial observations are not nodes of the candidate lattice")
-            self.lattice = None
-        if self.lattice is not None:
+        if self.persistent:
+            uniq, inv = torch.unique(self.theta, dim=0, return_inverse=True)
+            self.ktabY = ops.kernel_table_ysigned(uniq.contiguous(), self.kernel_id, self.lattice)
+            self.ktab_id = inv.to(i32).contiguous()
+            # trials that share a table run back to back on a CTA (the table is reloaded only when the slot changes)
+            self.order = (torch.sort(self.ktab_id, stable=True)[1].to(i32).contiguous() if uniq.shape[0] > 1 else None)
+            self.ws_loop = ops.bo_fixed_loop_workspace(T, self.lattice, dev)
+            self.fallback_trials = 0
+        elif self.lattice is not None:
             if self.fixed:
                 uniq, inv = torch.unique(self.theta, dim=0, return_inverse=True)
                 self.ktab = ops.kernel_table(uniq.contiguous(), self.kernel_id, self.lattice)
@@ -158,8 +179,9 @@ class BatchedBO:
         self.n.fill_(self.n0)
         self.status.zero_()
         self.nit.zero_()
-        self.alpha.zero_()
-        if self.append:
+        if self.alpha is not None:
+            self.alpha.zero_()
+        if self.append and self.wfrag is not None:
             self.wfrag.zero_()
         if self.theta_rest is not None:
             self._switch_theta(self.theta_first)
@@ -267,6 +289,8 @@ class BatchedBO:
         check_every == 0); later calls — after ``reset()`` with new initial sets of the same shape — replay it with
         one host call instead of ~6 launches per iteration. Latency lever for small batches (a single trial is
         launch-bound); identical results (same kernels, same order)."""
+        if self.persistent:
+            return self.run()                                  # already one launch for the whole run
         if self.check_every or self.theta_rest is not None:
             raise ops._lib.B200boError("run_graphed needs check_every=0 and no theta_rest (host logic inside the loop)")
         if getattr(self, "_graph", None) is None:
@@ -305,8 +329,33 @@ class BatchedBO:
         return BOResult(self.yall, self.picked[:, :self.max_iter], self.nit, self.status, self.X, self.y, self.n,
                         self.thetas)
 
+    def _run_persistent(self, check_fallback=True) -> BOResult:
+        """One launch for the whole batch (csrc/bo_persist.cu). Trials the kernel hands back (ST_FALLBACK: an appended
+        pivot was not positive, i.e. psd_safe_cholesky would have added jitter) are re-run through the per-iteration
+        kernels, which implement the jitter rule; that needs one host look at the status words."""
+        ops.bo_fixed_loop(self.lattice, self.ktabY, self.ktab_id, self.order, self.obj, self.surf_id, self.X, self.y, self.n,
+                          self.theta, self.best_f, self.yall, self.picked, self.nit, self.status, self.max_iter, self.acq_id,
+                          self.acq_param, self.var_floor, self.tol, self.optimal_y, ws=self.ws_loop)
+        self.launches += 1
+        self.iters_done = self.max_iter
+        if check_fallback:
+            fb = (self.status & ops.ST_FALLBACK) != 0
+            if bool(fb.any()):
+                idx = torch.nonzero(fb).flatten()
+                self.fallback_trials += int(idx.numel())
+                sub = BatchedBO(self.grid, self.obj, self.surf_id[idx], self.X[idx, :self.n0], self.y[idx, :self.n0],
+                                self.max_iter, theta=self.theta[idx], lattice=self.lattice, posterior="full", **self._kwargs)
+                r = sub.run()
+                for dst, src in ((self.yall, r.yall), (self.picked, sub.picked), (self.nit, r.nit), (self.X, r.X),
+                                 (self.y, r.y), (self.n, r.n), (self.best_f, sub.best_f), (self.status, r.status)):
+                    dst[idx] = src
+                self.launches += sub.launches
+        return BOResult(self.yall, self.picked[:, :self.max_iter], self.nit, self.status, self.X, self.y, self.n, None)
+
     @_on_device
     def run(self) -> BOResult:
+        if self.persistent:
+            return self._run_persistent()
         self._begin()
         for it in range(self.max_iter):
             self._advance(it)

@@ -14,7 +14,7 @@ from ._lib import check
 
 RBF, MATERN12, MATERN32, MATERN52 = 0, 1, 2, 3
 EI, UCB, PI = 0, 1, 2
-ST_JITTER, ST_CHOL_FAIL, ST_NONFINITE, ST_ALL_MASKED, ST_OFF_LATTICE = 1, 2, 4, 8, 16
+ST_JITTER, ST_CHOL_FAIL, ST_NONFINITE, ST_ALL_MASKED, ST_OFF_LATTICE, ST_FALLBACK = 1, 2, 4, 8, 16, 32
 NMAX = 128
 VAR_FLOOR = 1e-9          # botorch 0.8.0 analytic EI clamp
 
@@ -377,6 +377,52 @@ def grid_posterior_update_acq_argmax(lat, ktab2, ktab_id, X, wrow, zvec, n, thet
         _ptr(theta), _ptr(best_f), _ptr(mu_state), _ptr(ss_state), _ptr(obs_mask), _ptr(extra_mask), 1 if first else 0,
         1 if acquire else 0, int(acq_id), float(acq_param), float(var_floor), _ptr(arg_idx), _ptr(arg_val), _ptr(acq_out),
         _ptr(status), T, n_max, _ptr(ws), 0 if ws is None else ws.numel(), _stream()), "grid_posterior_update_acq_argmax")
+
+
+def kernel_table_ysigned(theta, kernel_id, lat, out=None):
+    """(H, 2Gy-1, Gx) f64 y-signed kernel table (input of the persistent fixed-theta loop, csrc/bo_persist.cu)."""
+    lib = _lib.load()
+    _cu(theta, torch.float64, "theta")
+    H = theta.shape[0]
+    if out is None:
+        out = torch.empty((H, 2 * lat.Gy - 1, lat.Gx), dtype=torch.float64, device=theta.device)
+    check(lib.b200bo_kernel_table_ysigned(_ptr(theta), H, int(kernel_id), lat.h, lat.Gx, lat.Gy, _ptr(out), _stream()),
+          "kernel_table_ysigned")
+    return out
+
+
+def bo_fixed_loop_supported(lat, n_max: int) -> bool:
+    """Does the lattice's kernel table (+ n_max rows of L^-1) fit one CTA's shared memory? Host-only."""
+    return bool(_lib.load().b200bo_bo_fixed_loop_supported(int(lat.Gx), int(lat.Gy), int(n_max)))
+
+
+def bo_fixed_loop_workspace(T: int, lat, device) -> torch.Tensor:
+    nbytes = int(_lib.load().b200bo_bo_fixed_loop_workspace_bytes(int(T), int(lat.Gx), int(lat.Gy)))
+    return torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+
+
+def bo_fixed_loop(lat, ktabY, ktab_id, order, obj, surf_id, X, y, n, theta, best_f, yall, picked, nit, status, max_iter,
+                  acq_id=EI, acq_param=0.0, var_floor=VAR_FLOOR, tol=0.1, optimal_y=100.0, ws=None):
+    """K-F: every iteration of every trial in ONE launch (BOloop_fixparam's loop, Src/BO.py:404-446). In place on
+    X / y / n / best_f / yall / picked / nit / status; trials flagged ST_FALLBACK come back untouched."""
+    lib = _lib.load()
+    _cu(ktabY, torch.float64, "ktabY"); _cu(obj, torch.float32, "obj"); _cu(surf_id, torch.int32, "surf_id")
+    _cu(X, torch.float64, "X"); _cu(y, torch.float64, "y"); _cu(n, torch.int32, "n"); _cu(theta, torch.float64, "theta")
+    _cu(best_f, torch.float64, "best_f"); _cu(yall, torch.float64, "yall"); _cu(picked, torch.int32, "picked")
+    _cu(nit, torch.int32, "nit"); _cu(status, torch.int32, "status")
+    if ktab_id is not None:
+        _cu(ktab_id, torch.int32, "ktab_id")
+    if order is not None:
+        _cu(order, torch.int32, "order")
+    T, n_max = y.shape
+    if ws is None:
+        ws = bo_fixed_loop_workspace(T, lat, X.device)
+    check(lib.b200bo_bo_fixed_loop(lat.Gx, lat.Gy, lat.x0, lat.y0, lat.h, _ptr(ktabY), _ptr(ktab_id), _ptr(order), _ptr(obj),
+                                   _ptr(surf_id), _ptr(X), _ptr(y), _ptr(n), _ptr(theta), _ptr(best_f), _ptr(yall),
+                                   _ptr(picked), _ptr(nit), _ptr(status), T, n_max, int(max_iter), int(acq_id),
+                                   float(acq_param), float(var_floor), float(tol), float(optimal_y), _ptr(ws), ws.numel(),
+                                   _stream()), "bo_fixed_loop")
+    return ws
 
 
 def gp_zvec(y, n, theta, wfrag, zvec):

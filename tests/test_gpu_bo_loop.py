@@ -187,3 +187,88 @@ def test_concurrent_groups_equal_one_batch(golden, lattice_grid, fit_mode):
         assert torch.equal(getattr(a, name), getattr(b, name)), name
     if fit_mode:
         assert torch.equal(a.thetas, b.thetas)
+
+
+@pytest.mark.parametrize("kid,acq", [(3, 0), (0, 0), (3, 1), (2, 2), (1, 0)])
+def test_persistent_loop_matches_oracle(golden, lattice_grid, kid, acq):
+    """posterior='persistent' (csrc/bo_persist.cu: every iteration of a trial inside one CTA, one launch per batch):
+    same picks, same curves, same observations as the oracle's full recomputation; reset() + second run identical."""
+    from b200bo import engine
+    T, n0, max_iter = 12, 10, 25
+    obj, surf_id, X0, y0 = _setup(golden, lattice_grid, T, n0, seed=kid * 10 + acq + 5)
+    theta = ogp.raw_to_theta(AUTHOR_THETA_RAW)
+    t = lambda a: torch.as_tensor(a, device=DEV)
+    bo = engine.BatchedBO(t(lattice_grid), t(obj), t(surf_id), t(X0), t(y0), max_iter, theta=t(theta), kernel_id=kid,
+                          acq_id=acq, acq_param=4.0, tol=0.1, posterior="persistent")
+    assert bo.persistent and bo.wfrag is None
+    for rep in range(2):
+        if rep:
+            bo.reset(t(X0), t(y0))
+        res = bo.run()
+        torch.cuda.synchronize()
+        assert res.status.max().item() == 0 and bo.launches == 1
+        early = 0
+        for i in range(T):
+            o = ogp.bo_loop(lattice_grid, obj[surf_id[i]], X0[i], y0[i], max_iter, theta=theta, kernel_id=kid, acq_id=acq,
+                            acq_param=4.0, tol=0.1)
+            nit = int(res.nit[i])
+            assert nit == o["nit"], (i, nit, o["nit"])
+            assert np.array_equal(res.picked[i, :nit].cpu().numpy(), o["idx"]), i
+            assert np.all(res.picked[i, nit:].cpu().numpy() == -1)
+            assert np.array_equal(res.yall[i].cpu().numpy(), o["yall"])
+            assert res.n[i].item() == n0 + nit
+            assert np.array_equal(res.X[i, :n0 + nit].cpu().numpy(), o["X"])
+            assert np.array_equal(res.y[i, :n0 + nit].cpu().numpy(), o["y"])
+            early += nit < max_iter
+        if acq == 0 and kid == 3:
+            assert early > 0
+
+
+def test_persistent_work_queue_and_table_switches_equal_full_recompute(golden, lattice_grid):
+    """More trials than CTAs (the work queue hands every CTA several trials) with three hyper-parameter rows (a CTA
+    reloads its shared-memory table when the slot changes): picks equal the full O(n^2) kernel's."""
+    from b200bo import engine
+    T, n0, max_iter = 400, 10, 40
+    obj, surf_id, X0, y0 = _setup(golden, lattice_grid, T, n0, seed=123)
+    base = ogp.raw_to_theta(AUTHOR_THETA_RAW)
+    rows = np.stack([base, base * np.array([2.0, 1.0, 0.7, 1.5]), base * np.array([0.5, 0.9, 1.3, 0.6])])
+    theta = rows[np.random.default_rng(5).integers(0, 3, T)]
+    t = lambda a: torch.as_tensor(a, device=DEV)
+    full = engine.BatchedBO(t(lattice_grid), t(obj), t(surf_id), t(X0), t(y0), max_iter, theta=t(theta), tol=-1.0).run()
+    bo = engine.BatchedBO(t(lattice_grid), t(obj), t(surf_id), t(X0), t(y0), max_iter, theta=t(theta), tol=-1.0,
+                          posterior="auto")
+    assert bo.persistent and bo.order is not None
+    per = bo.run()
+    torch.cuda.synchronize()
+    assert per.status.max().item() == 0 and torch.all(per.nit == max_iter)
+    same = (full.picked == per.picked).all(dim=1)
+    # identical posterior up to summation order; an arg-max can only differ on a rounding-level near-tie
+    assert same.float().mean().item() >= 0.99, same.float().mean().item()
+    assert torch.equal(full.yall[same], per.yall[same]) and torch.equal(full.X[same], per.X[same])
+
+
+def test_persistent_hands_non_positive_pivots_back_to_the_jitter_path(golden, lattice_grid):
+    """A duplicated initial point with (almost) no noise makes the appended pivot non-positive: the persistent kernel
+    flags the trial (ST_FALLBACK) and the engine re-runs it through the per-iteration kernels, whose Cholesky applies
+    psd_safe_cholesky's jitter — same result as posterior='full' for those trials, untouched neighbours unaffected."""
+    from b200bo import engine, ops
+    T, n0, max_iter = 6, 10, 12
+    obj, surf_id, X0, y0 = _setup(golden, lattice_grid, T, n0, seed=9)
+    X0[1, 7] = X0[1, 2]; y0[1, 7] = y0[1, 2]
+    X0[4, 9] = X0[4, 0]; y0[4, 9] = y0[4, 0]
+    theta = ogp.raw_to_theta(AUTHOR_THETA_RAW)
+    theta = np.array([0.0, theta[1], theta[2], theta[3]])               # no noise: K is exactly singular for trials 1, 4
+    t = lambda a: torch.as_tensor(a, device=DEV)
+    full = engine.BatchedBO(t(lattice_grid), t(obj), t(surf_id), t(X0), t(y0), max_iter, theta=t(theta), tol=-1.0).run()
+    bo = engine.BatchedBO(t(lattice_grid), t(obj), t(surf_id), t(X0), t(y0), max_iter, theta=t(theta), tol=-1.0,
+                          posterior="persistent")
+    per = bo.run()
+    torch.cuda.synchronize()
+    assert bo.fallback_trials == 2
+    st = per.status.cpu().numpy()
+    # (the full factorisation may see a rounding-level positive pivot where the rank-1 append sees <= 0: no jitter then)
+    assert not np.any(st & ops.ST_FALLBACK) and np.any(st[[1, 4]] & ops.ST_JITTER)
+    assert torch.equal(per.status[[1, 4]], full.status[[1, 4]])
+    assert torch.equal(per.picked[[1, 4]], full.picked[[1, 4]]) and torch.equal(per.yall[[1, 4]], full.yall[[1, 4]])
+    keep = [0, 2, 3, 5]
+    assert np.all(st[keep] == 0) and torch.equal(per.picked[keep], full.picked[keep])

@@ -1,7 +1,7 @@
 """Randomised differential test of the whole batched BO loop against the oracle: random lattice shapes / offsets /
 steps, kernels, acquisitions, hyper-parameters, initial-set sizes and iteration counts (fixed seeds). Picks, curves and
-iteration counts must be bit-identical; every posterior mode (full with / without rank-1 append, incremental) is run
-on the same case."""
+iteration counts must be bit-identical; every posterior mode (full with / without rank-1 append, incremental, and the
+persistent one-launch loop) is run on the same case."""
 import numpy as np
 import pytest
 import torch
@@ -49,11 +49,11 @@ def test_random_bo_loops_match_oracle(seed):
     ref = [ogp.bo_loop(c["grid"], c["obj"][c["sid"][i]], c["X0"][i], c["y0"][i], c["iters"], theta=c["theta"], kernel_id=c["kid"],
                        acq_id=c["acq"], acq_param=c["beta"], tol=c["tol"], optimal_y=float(c["obj"].max()))
            for i in range(len(c["sid"]))]
-    for mode in ("full-append", "full-refactor", "incremental"):
+    for mode in ("full-append", "full-refactor", "incremental", "persistent"):
         bo = engine.BatchedBO(t(c["grid"]), t(c["obj"]), t(c["sid"]), t(c["X0"]), t(c["y0"]), c["iters"], theta=t(c["theta"]),
                               kernel_id=c["kid"], acq_id=c["acq"], acq_param=c["beta"], tol=c["tol"],
                               optimal_y=float(c["obj"].max()), append=(mode != "full-refactor"),
-                              posterior="incremental" if mode == "incremental" else "full")
+                              posterior=mode if mode in ("incremental", "persistent") else "full")
         res = bo.run()
         torch.cuda.synchronize()
         nit = res.nit.cpu().numpy(); picked = res.picked.cpu().numpy(); yall = res.yall.cpu().numpy()

@@ -111,7 +111,7 @@ def _oracle_loops(key, grid, obj, surf_id, X0, y0, max_iter, theta, kid):
     return _ORACLE_CACHE[key]
 
 
-@pytest.mark.parametrize("posterior", ["full", "incremental"])
+@pytest.mark.parametrize("posterior", ["full", "incremental", "persistent"])
 @pytest.mark.parametrize("budget", [10000, 40000])
 def test_full_depth_fixed_theta_loop_matches_oracle(golden, lattice_grid, budget, posterior):
     """configs[3] / configs[4] depth: 100 iterations from 10 initial points (n -> 110, every NI / thread-count variant
@@ -134,8 +134,15 @@ def test_full_depth_fixed_theta_loop_matches_oracle(golden, lattice_grid, budget
         sid = torch.arange(2, dtype=torch.int32, device=DEV).repeat_interleave(40000)
         tab = ops.wildcat_eval(surfs, lat.points(DEV).repeat(2, 1), sid).reshape(2, -1).float()
         assert np.array_equal(tab.cpu().numpy(), obj)
+    if posterior == "persistent" and budget == 40000:
+        # the 200 x 200 table (638 KB) does not fit shared memory: explicit request refused, "auto" = full recomputation
+        with pytest.raises(ops._lib.B200boError):
+            engine.BatchedBO(_t(grid), _t(obj), _t(surf_id), _t(X0), _t(y0), max_iter, theta=_t(theta), kernel_id=kid,
+                             tol=-1.0, posterior="persistent")
+        posterior = "auto"
     bo = engine.BatchedBO(_t(grid), _t(obj), _t(surf_id), _t(X0), _t(y0), max_iter, theta=_t(theta), kernel_id=kid,
                           tol=-1.0, posterior=posterior)
+    assert bo.persistent == (posterior == "persistent")
     assert bo.lattice is not None and (bo.lattice.Gx, bo.lattice.h) == ((100, 1.0) if budget == 10000 else (200, 0.5))
     res = bo.run()
     torch.cuda.synchronize()
