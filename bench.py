@@ -4,10 +4,11 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (N > 1: launched by torchrun)
     python bench.py --impl reference [--steps K] [--warmup W]      CPU arm: the oracle port on the host cores
 
-Workload (BASELINE.json configs[4] shard, the largest single-GPU configuration): 12 500 independent BO
-trials per GPU (100 000 / 8) on synthetic Wildcat Wells instances, 10 random initial lattice points each,
-fixed GP hyper-parameters (the authors' fitted values), Matérn-5/2, EI over the 100 x 100 candidate
-lattice, 100 iterations, tol disabled so every trial runs all iterations.  One step = one full batch.
+Workload (BASELINE.json configs[4], the configuration the metric is quoted on; it fits one GPU): 100 000 independent BO
+trials on synthetic Wildcat Wells instances, sharded over the N GPUs (strong scaling: the same trials at every N),
+10 random initial lattice points each, fixed GP hyper-parameters (the authors' fitted values), Matérn-5/2, EI over the
+100 x 100 candidate lattice, 100 iterations, tol disabled so every trial runs all iterations, one final all-gather of
+the gap curves.  One step = the whole job once.
 metric = BO iterations per second (trials x iterations / time), whole job over all GPUs.
 """
 import argparse
@@ -43,7 +44,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--trials-per-gpu", type=int, default=12500)
+    ap.add_argument("--trials", type=int, default=100000,
+                    help="trials of the WHOLE job, sharded over the GPUs (BASELINE configs[4]: strong scaling)")
+    ap.add_argument("--trials-per-gpu", type=int, default=0,
+                    help="> 0: that many trials on every GPU instead (weak scaling)")
     ap.add_argument("--iters", type=int, default=100)
     ap.add_argument("--n0", type=int, default=10)
     ap.add_argument("--surfaces", type=int, default=256)
@@ -51,10 +55,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dpp", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the secondary configs[2]/configs[3] figures")
-    ap.add_argument("--posterior", default="full", choices=["full", "incremental"],
-                    help="full: O(n^2) fused recomputation per iteration (headline, north-star kernel); incremental: "
-                         "O(n) rank-1 posterior update per candidate with (mu, var) state in HBM")
-    ap.add_argument("--no-incremental-extra", action="store_true")
+    ap.add_argument("--posterior", default="auto", choices=["auto", "persistent", "full", "incremental"],
+                    help="auto / persistent: the whole loop of a trial in one CTA, O(n) posterior update per candidate, kernel "
+                         "table in shared memory (csrc/bo_persist.cu); full: O(n^2) fused recomputation per iteration (the "
+                         "north-star kernel K-B); incremental: O(n) update with the (mu, var) state in HBM")
+    ap.add_argument("--no-kb-extra", action="store_true", help="skip the K-B (posterior='full') slice beside the headline")
     return ap.parse_args()
 
 
@@ -124,8 +129,9 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "bo_iterations_per_s", "value": value, "unit": "BO iterations/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, args.steps),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "higher_is_better": True, "scaling": "strong" if total_trials(args, max(1, args.gpus))[1] else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, max(1, args.gpus)), "sample_trials_per_step": cores * args.cpu_trials_per_core,
         "cpu_baseline": {"value": value, "unit": "BO iterations/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "BO iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "restated oracle (oracle/gp.py), not the botorch path: botorch/gpytorch are not installable here",
@@ -133,13 +139,23 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def total_trials(args, world):
+    """(trials of the whole job, strong?) — default: BASELINE configs[4] as written, 100 000 trials sharded over the GPUs."""
+    if args.trials_per_gpu > 0:
+        return args.trials_per_gpu * world, False
+    return args.trials, True
+
+
 def workload_config(args, world):
-    return {"workload": "BASELINE configs[4] shard: fixed-theta BO trials on 2-D Wildcat Wells, EI over the 100x100 lattice",
-            "trials_per_gpu": args.trials_per_gpu, "trials_total": args.trials_per_gpu * world, "iterations": args.iters,
+    total, strong = total_trials(args, world)
+    return {"workload": "BASELINE configs[4]: fixed-theta BO trials on 2-D Wildcat Wells, EI over the 100x100 lattice, "
+                        "sharded over the GPUs, one final all-gather of the gap curves",
+            "trials_total": total, "iterations": args.iters,
             "n_init": args.n0, "grid": "100x100", "kernel": "matern52", "acquisition": "EI", "tol": "disabled",
             "hyperparameters": "fixed (authors' modes, smoothness 0.2 / ruggedness 0.2)", "surfaces": args.surfaces,
-            "l2_policy": "inputs larger than L2 (per-step working set ~0.7 GB of L^-1 fragments per GPU)",
-            "parallelism": f"trial-sharded x{world}, one final all-gather of gap curves"}
+            "l2_policy": "inputs larger than L2: every step streams a fresh batch's observations / curves / picks through HBM "
+                         "(0.4 GB per 100 000 trials) and rewrites every trial's per-candidate state",
+            "parallelism": f"trial-sharded x{world}" + (" (strong: the same trials at every N)" if strong else " (weak)")}
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -175,9 +191,44 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm)}
 
 
+def kb_full_roofline(prof, T, G, ms_total, peak, iters, extra=None):
+    """Roofline object of the fused O(n^2) grid posterior + EI + arg-max kernel (K-B) from the engine's per-launch events."""
+    from b200bo import ops
+    kb = [(n, e0.elapsed_time(e1)) for name, n, e0, e1 in prof if name == "grid_acq"]
+    ka = [(n, e0.elapsed_time(e1)) for name, n, e0, e1 in prof if name == "gp_chol"]
+    flops = sum(T * G * (n * n + 17 * n + 30) for n, _ in kb)
+    kb_ms = sum(ms for _, ms in kb)
+    ka_ms = sum(ms for _, ms in ka)
+    achieved = flops / (kb_ms * 1e-3) / 1e12 if kb_ms > 0 else 0.0
+    kb_avg_ms = kb_ms / max(1, len(kb))
+    bytes_mean = float(np.mean([T * (8 * ops.wfrag_doubles(n) + 24 * n + 56) for n, _ in kb])) if kb else None
+    out = {"bound": "tensor", "bound_detail": "FP64 tensor pipe: mma.sync.m8n8k4.f64 (DMMA), which shares the SM's FP64 "
+                                              "pipe with DFMA (profiles/fp64_peaks_r1.json); not HBM (see hbm_view)",
+           "kernel": "grid_acq_lattice8_kernel<NI,THREADS> (K-B, byte-coordinate lattice tile)", "achieved": achieved,
+           "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+           "hbm_view": {"algorithmic_bytes_per_launch_mean": bytes_mean,
+                        "achieved_gbs": bytes_mean / (kb_avg_ms * 1e-3) / 1e9 if kb else None},
+           "flops_model": "F_B = G (n^2 + 17 n + 30) per trial-iteration, exp/sqrt/erfc = 1 flop (SURVEY.md 8d)",
+           "kernel_share_of_step": kb_ms / ms_total if ms_total else None,
+           "gp_chol_share_of_step": ka_ms / ms_total if ms_total else None, "launches_timed": len(kb), "trials": T,
+           "frac_by_n": {str(n): round(T * G * (n * n + 17 * n + 30) / (ms * 1e-3) / 1e12 / peak, 3)
+                         for n, ms in kb[:iters] if n in (10, 16, 24, 32, 48, 64, 80, 96, 109)}}
+    out.update(extra or {})
+    return out
+
+
+def load_json(*parts):
+    try:
+        with open(os.path.join(ROOT, *parts)) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
+
+
 def run_b200(args):
     import torch
     from b200bo import dist, engine, ops
+    import BO
     import objectives
 
     rank, world, local = dist.init()
@@ -186,7 +237,10 @@ def run_b200(args):
             raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    T, iters, n0, S = args.trials_per_gpu, args.iters, args.n0, args.surfaces
+    iters, n0, S = args.iters, args.n0, args.surfaces
+    total, strong = total_trials(args, world)
+    lo, hi = dist.shard_range(total, rank, world)
+    T = hi - lo
     lat = ops.Lattice(100, 100)
     grid = lat.points(dev)
     G = lat.G
@@ -196,40 +250,42 @@ def run_b200(args):
     gen.device = str(dev)
     seeds = [s // 16 for s in range(S)]
     fam = [FAMILIES[s % 16] for s in range(S)]
-    surf = gen.wildcatwells_batch(seeds, [f[0] for f in fam], [f[1] for f in fam], device=dev)
+    make_surfaces = lambda: gen.wildcatwells_batch(seeds, [f[0] for f in fam], [f[1] for f in fam], device=dev)
+    surf = make_surfaces()
     obj_dev = surf[:, :100, :100].reshape(S, G).contiguous()
-    lo, hi = dist.shard_range(T * world, rank, world)
-    idx0 = init_sets(T, n0, 12345 + rank)
-    surf_id_h = ((np.arange(lo, hi)) % S).astype(np.int32)
+    # the whole job's initial sets (a function of the global trial index: every N runs the same 100 000 trials)
+    idx_all = init_sets(total, n0, 12345)
+    sid_all = (np.arange(total) % S).astype(np.int32)
     grid_h = grid.cpu().numpy()
     obj_h = obj_dev.cpu().numpy()
-    X0_h = torch.from_numpy(grid_h[idx0]).pin_memory()
-    y0_h = torch.from_numpy(obj_h[surf_id_h[:, None], idx0].astype(np.float64)).pin_memory()
-    sid_h = torch.from_numpy(surf_id_h).pin_memory()
-    objp_h = torch.from_numpy(obj_h).pin_memory()
-    X0_d, y0_d, sid_d = X0_h.to(dev), y0_h.to(dev), sid_h.to(dev)
+    X0_all = torch.from_numpy(grid_h[idx_all]).pin_memory()
+    y0_all = torch.from_numpy(obj_h[sid_all[:, None], idx_all].astype(np.float64)).pin_memory()
+    sid_allt = torch.from_numpy(sid_all).pin_memory()
+    X0_d, y0_d, sid_d = X0_all[lo:hi].to(dev), y0_all[lo:hi].to(dev), sid_allt[lo:hi].to(dev)
     theta = torch.tensor(THETA, dtype=torch.float64, device=dev)
 
     bo = engine.BatchedBO(grid, obj_dev, sid_d, X0_d, y0_d, iters, theta=theta, kernel_id=ops.MATERN52, acq_id=ops.EI,
                           tol=-1.0, lattice=lat, check_every=0, posterior=args.posterior)
-    yall_host = torch.empty((T, iters + 2), dtype=torch.float64).pin_memory()
-    nit_host = torch.empty(T, dtype=torch.int32).pin_memory()
+    mode = "persistent" if bo.persistent else ("incremental" if bo.incremental else "full")
+    yall_host = torch.empty((total, iters + 2), dtype=torch.float64).pin_memory()
+    nit_host = torch.empty(total, dtype=torch.int32).pin_memory()
 
     def step_resident():
         bo.reset(X0_d, y0_d)
         res = bo.run()
-        curves = dist.gather_curves(res.yall)            # the path's only exchange (N > 1)
+        curves = dist.gather_curves(res.yall, dist.shard_counts(total, world))    # the path's only exchange (N > 1)
         return res, curves
 
     def step_e2e():
-        bo.obj.copy_(objp_h, non_blocking=True)          # host buffers -> device, every step
-        bo.reset(X0_h, y0_h, sid_h)
-        res = bo.run()
-        curves = dist.gather_curves(res.yall)
+        # what a user of the reference-facing module calls, host buffers in, host curves out: surfaces (K-E), the batched
+        # BO entry (engine construction, kernel table, H2D of this rank's initial sets, the loop, the gather), D2H
+        table = make_surfaces()[:, :100, :100].reshape(S, G).contiguous()
+        res = BO.BOloop_batched(table, sid_allt, X0_all, y0_all, iters, theta=np.asarray(THETA), grid=lat, tol=-1.0,
+                                device=str(dev), posterior=args.posterior, devices="ranks")
         yall_host.copy_(res.yall, non_blocking=True)
         nit_host.copy_(res.nit, non_blocking=True)
         torch.cuda.synchronize(dev)
-        return res, curves
+        return res, res.yall
 
     def timed(fn, k):
         dist.barrier(dev)
@@ -247,16 +303,13 @@ def run_b200(args):
     for _ in range(args.warmup):
         step_resident()
     torch.cuda.synchronize(dev)
-    # roofline denominator: FP64 FMA issue rate measured now (GPU warm), never below the committed
-    # micro-benchmark of this pool's B200 (profiles/fp64_peaks_r1.json: DFMA and DMMA share the pipe)
+    # roofline denominators measured now (GPU warm): FP64 FMA issue rate (never below the committed micro-benchmark of
+    # this pool's B200, profiles/fp64_peaks_r1.json: DFMA and DMMA share the pipe) and shared-memory read bandwidth
     peak_probe = ops.fp64_fma_peak_tflops(dev)
-    peak_file = None
-    try:
-        pf = json.load(open(os.path.join(ROOT, "profiles", "fp64_peaks_r1.json")))
-        peak_file = max(pf.get("dfma_tflops", 0.0), pf.get("dmma_tflops_acc4", 0.0))
-    except Exception:
-        pass
-    peak = max(peak_probe, peak_file or 0.0)
+    pf = load_json("profiles", "fp64_peaks_r1.json") or {}
+    peak_file = max(pf.get("dfma_tflops", 0.0), pf.get("dmma_tflops_acc4", 0.0)) or None
+    fp64_peak = max(peak_probe, peak_file or 0.0)
+    smem_peak = ops.smem_lds_peak_gbs(dev)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -268,99 +321,101 @@ def run_b200(args):
     launches = bo.launches * args.steps
     nit_sum = int(res.nit.sum().item())
     status_max = int(res.status.max().item())
-    ms_e2e, _ = timed(step_e2e, args.steps)
+    picked_headline = res.picked[:1480].clone()
+    for _ in range(1):
+        step_e2e()
+    ms_e2e, (res_e2e, _) = timed(step_e2e, args.steps)
+    e2e_same = bool(torch.equal(res_e2e.yall[lo:hi], res.yall))
 
-    # ---- roofline of the dominant kernel (fused grid posterior + EI + arg-max), measured in the timed steps
-    kb = [(n, e0.elapsed_time(e1)) for name, n, e0, e1 in prof if name == "grid_acq"]
-    ka = [(n, e0.elapsed_time(e1)) for name, n, e0, e1 in prof if name == "gp_chol"]
-    ki = [(n, e0.elapsed_time(e1)) for name, n, e0, e1 in prof if name == "grid_inc"]
-    flops = sum(T * G * (n * n + 17 * n + 30) for n, _ in kb)
-    kb_ms = sum(ms for _, ms in kb)
-    ka_ms = sum(ms for _, ms in ka)
-    achieved = flops / (kb_ms * 1e-3) / 1e12 if kb_ms > 0 else 0.0
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_grid_acq_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    hbm_peak_gbs = None
-    try:
-        hbm_peak_gbs = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
-    except Exception:
-        pass
-    kb_avg_ms = kb_ms / max(1, len(kb))
-    roofline = {"bound": "tensor", "bound_detail": "FP64 tensor pipe: mma.sync.m8n8k4.f64 (DMMA), which shares the SM's FP64 "
-                                                   "pipe with DFMA (profiles/fp64_peaks_r1.json); not HBM (see hbm_view)",
-                "kernel": "grid_acq_lattice8_kernel<NI,THREADS> (K-B, byte-coordinate lattice tile)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak if peak else None, "traffic": traffic,
-                "hbm_view": {"algorithmic_bytes_per_launch_mean": float(np.mean([T * (8 * ops.wfrag_doubles(n) + 24 * n + 56) for n, _ in kb])) if kb else None,
-                             "achieved_gbs": (float(np.mean([T * (8 * ops.wfrag_doubles(n) + 24 * n + 56) for n, _ in kb])) / (kb_avg_ms * 1e-3) / 1e9) if kb else None,
-                             "peak_gbs_of_measured": hbm_peak_gbs},
-                "peak_probe_this_run": peak_probe, "peak_microbench_file": peak_file,
-                "peak_source": "max(FP64 FMA issue rate measured in this run by b200bo_fp64_fma_probe, DFMA/DMMA rate of "
-                               "tools/microbench/fp64_peaks.cu committed in profiles/fp64_peaks_r1.json); DMMA and DFMA share "
-                               "one pipe. MEASURED_PEAKS.json holds HBM / bf16 only.",
-                "flops_model": "F_B = G (n^2 + 17 n + 30) per trial-iteration, exp/sqrt/erfc = 1 flop (SURVEY.md 8d)",
-                "kernel_share_of_step": kb_ms / ms_total if ms_total else None,
-                "gp_chol_share_of_step": ka_ms / ms_total if ms_total else None,
-                "launches_timed": len(kb),
-                "frac_by_n": {str(n): round(T * G * (n * n + 17 * n + 30) / (ms * 1e-3) / 1e12 / peak, 3)
-                              for n, ms in kb[:iters] if n in (10, 16, 24, 32, 48, 64, 80, 96, 109)}}
-
-    if args.posterior == "incremental":
+    hbm_peak_gbs = (load_json("MEASURED_PEAKS.json") or {}).get("hbm_gbs")
+    if mode == "persistent":
+        # dominant kernel = bo_fixed_loop_kernel (K-F). Its hot loop is ONE 8-byte kernel-table look-up out of shared
+        # memory per (candidate, observation) pair of every appended row: G * R (R + 1) / 2 look-ups per trial,
+        # R = n0 + nit - 1 rows folded. Roofline = shared-memory read bandwidth (128 B / clk / SM), measured above.
+        kf_ms = sum(e0.elapsed_time(e1) for name, n, e0, e1 in prof if name == "bo_fixed_loop")
+        R = (res.nit.to(torch.int64) + (n0 - 1))
+        lookups = int((R * (R + 1) // 2).sum().item()) * G
+        nl = max(1, sum(1 for name, *_ in prof if name == "bo_fixed_loop"))
+        bytes_per_launch = 8.0 * lookups
+        ach = bytes_per_launch * nl / (kf_ms * 1e-3) / 1e9 if kf_ms > 0 else 0.0
+        tr = load_json("profiles", "r2_kf_traffic.json") or {}
+        # HBM view: per trial the kernel reads 24 n0 + 36 B of inputs, the objective value of each pick, and writes
+        # 24 nit + 8 (max_iter + 2) + 4 max_iter + 16 B of results; the per-candidate state stays in L2
+        hbm_bytes = T * (24 * n0 + 36 + 4 * iters + 24 * iters + 8 * (iters + 2) + 4 * iters + 16)
+        roofline = {"bound": "smem", "bound_detail": "shared-memory read bandwidth (LDS.64, 128 B/clk/SM): the kernel table "
+                    "lives in shared memory and the loop is one 8-byte look-up + one DFMA per (candidate, observation) pair; "
+                    "neither HBM (hbm_view) nor the FP64 pipe (fp64_view) is near its limit",
+                    "kernel": "bo_fixed_loop_kernel<100,10> (K-F, csrc/bo_persist.cu)", "achieved": ach, "peak": smem_peak,
+                    "unit": "GB/s", "frac": ach / smem_peak if smem_peak else None,
+                    "peak_source": "b200bo_smem_lds_probe measured in this run (conflict-free LDS.64, one 1024-thread CTA per "
+                                   "SM); nominal 128 B/clk/SM x 148 SMs x SM clock",
+                    "bytes_model": "8 B x G x R (R + 1) / 2 per trial, R = n0 + nit - 1 appended rows (SURVEY.md 8d counts "
+                                   "the O(n^2) recomputation; this kernel updates the same posterior in O(n) per candidate)",
+                    "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": kf_ms / nl,
+                    "traffic": tr.get("dram_bytes_per_trial", None) and tr["dram_bytes_per_trial"] * T,
+                    "traffic_source": tr.get("source"),
+                    "hbm_view": {"algorithmic_bytes_per_launch": hbm_bytes,
+                                 "achieved_gbs": hbm_bytes * nl / (kf_ms * 1e-3) / 1e9 if kf_ms else None,
+                                 "peak_gbs_of_measured": hbm_peak_gbs},
+                    "fp64_view": {"dfma_per_lookup": 1, "achieved_tflops": 2.0 * lookups * nl / (kf_ms * 1e-3) / 1e12 if kf_ms else None,
+                                  "peak_tflops": fp64_peak},
+                    "kernel_share_of_step": kf_ms / ms_total if ms_total else None, "launches_timed": nl}
+    elif mode == "incremental":
         # dominant kernel = grid_inc_kernel (+ the row append inside the same timed bracket): HBM-side model
         # 32 B per candidate and launch (read + write of the two fp64 state words), first launch writes only
+        ki = [(n, e0.elapsed_time(e1)) for name, n, e0, e1 in prof if name == "grid_inc"]
         ki_ms = sum(ms for _, ms in ki)
         hbm_bytes = sum(T * G * (16 if n == 1 else 32) for n, _ in ki)
-        hbm_peak = None
-        try:
-            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
-        except Exception:
-            pass
-        hbm_peak = hbm_peak or 6650.0
+        hbm_peak = hbm_peak_gbs or 6650.0
         ach = hbm_bytes / (ki_ms * 1e-3) / 1e9 if ki_ms > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": "grid_inc_kernel (incremental K-B) + gp_append_kernel", "achieved": ach,
                     "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
                     "bytes_model": "32 B per candidate-iteration (two fp64 state words read + written)",
                     "note": "issue-bound above n ~ 20 (n table look-ups + n FMA per candidate), HBM-bound below",
                     "kernel_share_of_step": ki_ms / ms_total if ms_total else None, "launches_timed": len(ki)}
-    total_its = nit_sum * world            # every rank runs the same number of trial-iterations (tol disabled)
+    else:
+        tr = load_json("profiles", "r1_grid_acq_traffic.json") or {}
+        roofline = kb_full_roofline(prof, T, G, ms_total, fp64_peak, iters,
+                                    {"traffic": tr.get("dram_bytes_per_launch"), "traffic_trials": tr.get("trials"),
+                                     "peak_probe_this_run": peak_probe, "peak_microbench_file": peak_file})
+    total_its = int(dist.sum_over_ranks(nit_sum, dev))
     per_step_ms = ms_total / args.steps
     value = total_its / (per_step_ms * 1e-3)
     e2e_val = total_its / (ms_e2e / args.steps * 1e-3)
-    h2d = X0_h.numel() * 8 + y0_h.numel() * 8 + sid_h.numel() * 4 + objp_h.numel() * 4
+    h2d = (X0_all[lo:hi].numel() * 8 + y0_all[lo:hi].numel() * 8 + sid_allt[lo:hi].numel() * 4) * 1
     d2h = yall_host.numel() * 8 + nit_host.numel() * 4
 
     line = {"metric": "bo_iterations_per_s", "value": value, "unit": "BO iterations/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": per_step_ms, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, world), "roofline": roofline,
             "e2e": {"value": e2e_val, "unit": "BO iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps, "bytes_are": "per rank",
+                    "entry": "objectives.wildcatwells_batch -> BO.BOloop_batched(host arrays, devices='ranks') -> curves on the host",
+                    "same_curves_as_resident_run": e2e_same},
+            "engine": {"posterior": mode, "trials_this_rank": T},
             "gpu_launches": int(launches), "clocks": clocks, "status_bits_seen": status_max,
             "gathered_curves_shape": list(curves.shape)}
 
-    line["config"]["posterior"] = args.posterior
-    if rank == 0 and world == 1 and args.posterior == "full" and not args.no_incremental_extra:
-        # the same workload through the O(n) incremental posterior (not the headline: see DESIGN.md §3)
-        del bo
-        torch.cuda.empty_cache()
-        bo2 = engine.BatchedBO(grid, obj_dev, sid_d, X0_d, y0_d, iters, theta=theta, kernel_id=ops.MATERN52,
-                               acq_id=ops.EI, tol=-1.0, lattice=lat, check_every=0, posterior="incremental")
+    if rank == 0 and world == 1 and mode == "persistent" and not args.no_kb_extra:
+        # the north-star kernel itself — the fused O(n^2) grid posterior + EI + arg-max (K-B) — on a slice of the same
+        # workload, against the FP64 pipe; and its picks beside the headline path's
+        Tk = min(T, 1480)
+        bo2 = engine.BatchedBO(grid, obj_dev, sid_d[:Tk], X0_d[:Tk], y0_d[:Tk], iters, theta=theta, kernel_id=ops.MATERN52,
+                               acq_id=ops.EI, tol=-1.0, lattice=lat, check_every=0, posterior="full")
 
-        def step_inc():
-            bo2.reset(X0_d, y0_d)
+        def step_full():
+            bo2.reset(X0_d[:Tk], y0_d[:Tk])
             return bo2.run()
 
-        for _ in range(max(1, args.warmup)):
-            r2 = step_inc()
-        ms_inc, r2 = timed(step_inc, args.steps)
-        agree = float((r2.picked == res.picked).all(dim=1).float().mean().item())
-        line["incremental"] = {"value": int(r2.nit.sum().item()) / (ms_inc / args.steps * 1e-3), "unit": "BO iterations/s",
-                               "ms_per_step": ms_inc / args.steps, "trials_with_identical_picks": agree,
-                               "note": "posterior='incremental': rank-1 update of (mu, var) per candidate, state in HBM; "
-                                       "same posterior as the headline path"}
+        step_full()
+        bo2.profile = []
+        ms_full, r2 = timed(step_full, 1)
+        kb = kb_full_roofline(bo2.profile, Tk, G, ms_full, fp64_peak, iters)
+        kb["value"] = int(r2.nit.sum().item()) / (ms_full * 1e-3)
+        kb["unit_value"] = "BO iterations/s"
+        kb["trials_with_identical_picks_vs_headline"] = float((r2.picked == picked_headline[:Tk]).all(dim=1).float().mean().item())
+        line["kb_full"] = kb
         del bo2
     if rank == 0 and world == 1 and not args.no_dpp:
         line["dpp"] = bench_dpp(dev)

@@ -56,6 +56,9 @@ int b200bo_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * launches blocks x 256 threads x iters x 8 dependent-chain FMAs, writes blocks*256 doubles to out,
  * returns the flop count issued (> 0) or -(error code). */
 long long b200bo_fp64_fma_probe(double* out, int blocks, int iters, void* stream);
+/* shared-memory read bandwidth (conflict-free LDS.64, 1024 threads per CTA): out (blocks*1024) f64 scratch; returns the
+ * bytes read (< 0: error). Roofline denominator of b200bo_bo_fixed_loop. */
+long long b200bo_smem_lds_probe(double* out, int blocks, int iters, void* stream);
 
 /* ---- K-D  ranked-DPP set score -------------------------------------------------
  * replaces diverse_data_generator.twoD_score looped over the superset,

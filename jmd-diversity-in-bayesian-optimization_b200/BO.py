@@ -214,22 +214,65 @@ def _fixparam_to_theta(fixparam):
 
 def BOloop_batched(obj_tables, surf_id, init_X, init_y, max_iter, theta=None, grid=None, acq="EI", acq_param=0.0,
                    tol=0.1, optimal_y=100.0, nu=2.5, covar="matern", device="cuda:0", lattice="auto", theta_rest=None,
-                   posterior="full", groups="auto"):
-    """Native batched entry: T trials in lock-step. obj_tables (S,G) f32 objective at every candidate, surf_id (T,),
+                   posterior="auto", groups="auto", devices=None):
+    """Native batched entry: T independent trials. obj_tables (S,G) f32 objective at every candidate, surf_id (T,),
     init_X (T,n0,2), init_y (T,n0); theta (4,) / (T,4) ACTUAL hyper-parameters or None (= fit before every
-    acquisition). posterior="incremental" (fixed theta, lattice candidates): O(n) posterior update per candidate. grid: (G,2) candidates or an ops.Lattice (default: the 100x100 lattice of data_gen.constructX).
-    groups > 1 cuts the batch into that many contiguous groups advanced concurrently on separate CUDA streams (same
-    results trial by trial; pays when theta is None and the per-iteration fit has a long tail: b200bo.engine.run_concurrent);
-    "auto" = 3 groups for fitted batches of at least 384 trials, else 1.
+    acquisition). grid: (G,2) candidates or an ops.Lattice (default: the 100x100 lattice of data_gen.constructX).
+    posterior: "auto" = the one-launch persistent loop (csrc/bo_persist.cu) when theta is fixed and the lattice's kernel
+    table fits shared memory, else "full" (O(n^2) fused recomputation per iteration); "incremental": O(n) update per
+    candidate with the state in HBM. groups > 1 cuts the batch into that many contiguous groups advanced concurrently on
+    separate CUDA streams (pays when theta is None and the per-iteration fit has a long tail:
+    b200bo.engine.run_concurrent); "auto" = 3 groups for fitted batches of at least 384 trials, else 1.
+    devices — where the trials run (they are independent; the reference fans them out over ipyparallel engines,
+    Scripts/Experiment2.py:75-92,110-141):
+      None             all T trials on ``device``;
+      ["cuda:0", ...]  contiguous trial ranges on several GPUs of this process, driven from this host thread (one stream
+                       per GPU); the result is concatenated on the first device;
+      "ranks"          one process per GPU under torchrun: this rank runs its range (b200bo.dist.shard_range) on
+                       ``device`` and every rank returns the all-gathered result of the whole batch.
+    Whatever the split, the result equals the single-device result trial for trial.
     Returns b200bo.engine.BOResult (device tensors)."""
-    with torch.cuda.device(torch.device(device)):
-        return _boloop_batched(obj_tables, surf_id, init_X, init_y, max_iter, theta, grid, acq, acq_param, tol, optimal_y,
-                               nu, covar, torch.device(device), lattice, theta_rest, posterior, groups)
+    common = dict(max_iter=max_iter, grid=grid, acq=acq, acq_param=acq_param, tol=tol, optimal_y=optimal_y, nu=nu,
+                  covar=covar, lattice=lattice, posterior=posterior, groups=groups)
+    T = int(np.shape(init_y)[0])
+    cut = lambda a, lo, hi: a if a is None or (np.ndim(a) == 1 and np.shape(a)[0] == 4) else a[lo:hi]
+
+    def shard(lo, hi, dev, **kw):
+        with torch.cuda.device(dev):
+            return _boloop_batched(obj_tables, surf_id[lo:hi], init_X[lo:hi], init_y[lo:hi], theta=cut(theta, lo, hi),
+                                   theta_rest=cut(theta_rest, lo, hi), dev=dev, **common, **kw)
+
+    fields = ("yall", "picked", "nit", "status", "X", "y", "n", "thetas")
+    if isinstance(devices, str) and devices == "ranks":
+        from b200bo import dist as bdist
+        dev = torch.device(device)
+
+        def run_local(lo, hi):
+            r = shard(lo, hi, dev)[0]
+            return {f: getattr(r, f) for f in fields}
+        return engine.BOResult(**bdist.run_sharded(T, run_local))
+    if devices is not None:
+        from b200bo import dist as bdist
+        devs = [torch.device(d) for d in devices]
+        bos = []
+        for k, dev in enumerate(devs):
+            lo, hi = bdist.shard_range(T, k, len(devs))
+            if hi > lo:
+                bos += shard(lo, hi, dev, build_only=True)
+        res = engine.run_concurrent(bos)
+        first = devs[0]
+        out = engine.concat_results([engine.BOResult(**{f: (None if getattr(r, f) is None else getattr(r, f).to(first))
+                                                        for f in fields}) for r in res])
+        for dev in devs:
+            torch.cuda.synchronize(dev)
+        return out
+    return shard(0, T, torch.device(device))[0]
 
 
 def _boloop_batched(obj_tables, surf_id, init_X, init_y, max_iter, theta, grid, acq, acq_param, tol, optimal_y, nu, covar,
-                    dev, lattice, theta_rest, posterior, groups):
-    t = lambda a, dt: torch.as_tensor(a, dtype=dt).to(dev).contiguous()
+                    lattice, theta_rest, posterior, groups, dev, build_only=False):
+    """One device. Returns [BOResult], or with build_only the list of BatchedBO groups (not yet run)."""
+    t = lambda a, dt: torch.as_tensor(a, dtype=dt).to(dev, non_blocking=True).contiguous()
     if grid is None:
         grid = ops.Lattice(100, 100)
     lat = grid if isinstance(grid, ops.Lattice) else lattice
@@ -252,10 +295,13 @@ def _boloop_batched(obj_tables, surf_id, init_X, init_y, max_iter, theta, grid, 
     if groups == "auto":                                   # measured on 1 000 / 4 000 trials: +8..22 % with a fit per iteration
         groups = 3 if (theta is None and T >= 384) else 1
     groups = max(1, min(int(groups), T))
-    if groups == 1:
-        return make(0, T).run()
     cuts = [T * g // groups for g in range(groups + 1)]
-    return engine.concat_results(engine.run_concurrent([make(cuts[g], cuts[g + 1]) for g in range(groups)]))
+    bos = [make(cuts[g], cuts[g + 1]) for g in range(groups)]
+    if build_only:
+        return bos
+    if groups == 1:
+        return [bos[0].run()]
+    return [engine.concat_results(engine.run_concurrent(bos))]
 
 
 def _single(obj_func, max_iter, X, Y, theta, bounds, tol, nu, covar, minstate, optimal_y, budget, device,

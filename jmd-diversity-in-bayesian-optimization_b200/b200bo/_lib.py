@@ -28,6 +28,7 @@ PROTOTYPES = {
     "b200bo_mt_seeded_randbelow": (c_int, [P, c_longlong, c_uint64, c_uint64, P, P, P, P]),
     "b200bo_wildcat_surface": (c_int, [P, P, P, P, P, P, c_int, P]),
     "b200bo_fp64_fma_probe": (c_longlong, [P, c_int, c_int, P]),
+    "b200bo_smem_lds_probe": (c_longlong, [P, c_int, c_int, P]),
     "b200bo_wildcat_eval": (c_int, [P, P, P, P, P, c_longlong, P]),
     "b200bo_simplex_noise": (c_int, [c_uint64, P, P, P, c_longlong, P]),
     "b200bo_wfrag_doubles": (c_size_t, [c_int]),

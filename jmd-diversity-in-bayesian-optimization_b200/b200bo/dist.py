@@ -58,12 +58,45 @@ def gather_curves(local: torch.Tensor, counts=None) -> torch.Tensor:
     return torch.cat([out[r * mx:r * mx + counts[r]] for r in range(world)])
 
 
+def shard_counts(total: int, world: int):
+    """Shard sizes in rank order (a pure function of (total, world): no collective needed to know them)."""
+    return [hi - lo for lo, hi in (shard_range(total, r, world) for r in range(world))]
+
+
+def run_sharded(total: int, run_local, rank=None, world=None):
+    """The multi-GPU form of a batch of independent trials (replaces the ipyparallel fan-out of
+    Scripts/Experiment2.py:75-92,110-141): this rank runs ``run_local(lo, hi)`` on its contiguous trial range — a dict
+    name -> tensor whose leading dimension is hi - lo — and every tensor is all-gathered in rank order, so each rank
+    returns the result of the whole batch, trial for trial what one process computes on all of it. No collective on
+    the data path; one gather per result tensor at the end."""
+    if rank is None or world is None:
+        r, w, _ = env_rank_world()
+        if dist.is_initialized():
+            r, w = dist.get_rank(), dist.get_world_size()
+        rank, world = (r if rank is None else rank), (w if world is None else world)
+    lo, hi = shard_range(total, rank, world)
+    local = run_local(lo, hi)
+    if world == 1:
+        return local
+    counts = shard_counts(total, world)
+    return {k: (None if v is None else gather_curves(v, counts)) for k, v in local.items()}
+
+
 def max_over_ranks(value: float, device) -> float:
     """Max of a per-rank scalar (timings are reported as the slowest rank)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return float(value)
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, device) -> float:
+    """Sum of a per-rank scalar (e.g. the iterations every rank ran)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
 
 

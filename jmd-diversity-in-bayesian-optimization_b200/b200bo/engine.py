@@ -308,11 +308,15 @@ class BatchedBO:
 
     @_on_device
     def _begin(self):
+        if self.persistent:
+            return self._launch_persistent()
         ops.bo_init(self.y, self.n, self.best_f, self.yall, self.picked, self.nit, self.max_iter, self.tol, self.optimal_y)
         self.launches += 1
 
     @_on_device
     def _advance(self, it: int):
+        if self.persistent:
+            return                                             # every iteration already runs inside the one launch
         if self.incremental:
             self._step_incremental(it)
         else:
@@ -321,6 +325,8 @@ class BatchedBO:
 
     @_on_device
     def _end(self) -> BOResult:
+        if self.persistent:
+            return self._finish_persistent()
         if not self.fixed and self.iters_done > 0:
             # the model re-created after the LAST append is fitted and recorded too (Src/BO.py:176-189,252)
             self._timed("fit", self.n0 + self.iters_done, lambda: self._fit(self.iters_done, self.n0 + self.iters_done))
@@ -329,35 +335,36 @@ class BatchedBO:
         return BOResult(self.yall, self.picked[:, :self.max_iter], self.nit, self.status, self.X, self.y, self.n,
                         self.thetas)
 
-    def _run_persistent(self, check_fallback=True) -> BOResult:
-        """One launch for the whole batch (csrc/bo_persist.cu). Trials the kernel hands back (ST_FALLBACK: an appended
-        pivot was not positive, i.e. psd_safe_cholesky would have added jitter) are re-run through the per-iteration
-        kernels, which implement the jitter rule; that needs one host look at the status words."""
-        ops.bo_fixed_loop(self.lattice, self.ktabY, self.ktab_id, self.order, self.obj, self.surf_id, self.X, self.y, self.n,
-                          self.theta, self.best_f, self.yall, self.picked, self.nit, self.status, self.max_iter, self.acq_id,
-                          self.acq_param, self.var_floor, self.tol, self.optimal_y, ws=self.ws_loop)
+    def _launch_persistent(self):
+        """One launch for the whole batch (csrc/bo_persist.cu); asynchronous, no host look at the results."""
+        self._timed("bo_fixed_loop", self.n_max, lambda: ops.bo_fixed_loop(
+            self.lattice, self.ktabY, self.ktab_id, self.order, self.obj, self.surf_id, self.X, self.y, self.n, self.theta,
+            self.best_f, self.yall, self.picked, self.nit, self.status, self.max_iter, self.acq_id, self.acq_param,
+            self.var_floor, self.tol, self.optimal_y, ws=self.ws_loop))
         self.launches += 1
         self.iters_done = self.max_iter
-        if check_fallback:
-            fb = (self.status & ops.ST_FALLBACK) != 0
-            if bool(fb.any()):
-                idx = torch.nonzero(fb).flatten()
-                self.fallback_trials += int(idx.numel())
-                sub = BatchedBO(self.grid, self.obj, self.surf_id[idx], self.X[idx, :self.n0], self.y[idx, :self.n0],
-                                self.max_iter, theta=self.theta[idx], lattice=self.lattice, posterior="full", **self._kwargs)
-                r = sub.run()
-                for dst, src in ((self.yall, r.yall), (self.picked, sub.picked), (self.nit, r.nit), (self.X, r.X),
-                                 (self.y, r.y), (self.n, r.n), (self.best_f, sub.best_f), (self.status, r.status)):
-                    dst[idx] = src
-                self.launches += sub.launches
+
+    def _finish_persistent(self) -> BOResult:
+        """Trials the kernel handed back (ST_FALLBACK: an appended pivot was not positive, i.e. psd_safe_cholesky would
+        have added jitter) are re-run through the per-iteration kernels, which implement the jitter rule; that needs one
+        host look at the status words (the only synchronisation of the persistent path)."""
+        fb = (self.status & ops.ST_FALLBACK) != 0
+        if bool(fb.any()):
+            idx = torch.nonzero(fb).flatten()
+            self.fallback_trials += int(idx.numel())
+            sub = BatchedBO(self.grid, self.obj, self.surf_id[idx], self.X[idx, :self.n0], self.y[idx, :self.n0],
+                            self.max_iter, theta=self.theta[idx], lattice=self.lattice, posterior="full", **self._kwargs)
+            r = sub.run()
+            for dst, src in ((self.yall, r.yall), (self.picked, sub.picked), (self.nit, r.nit), (self.X, r.X),
+                             (self.y, r.y), (self.n, r.n), (self.best_f, sub.best_f), (self.status, r.status)):
+                dst[idx] = src
+            self.launches += sub.launches
         return BOResult(self.yall, self.picked[:, :self.max_iter], self.nit, self.status, self.X, self.y, self.n, None)
 
     @_on_device
     def run(self) -> BOResult:
-        if self.persistent:
-            return self._run_persistent()
         self._begin()
-        for it in range(self.max_iter):
+        for it in range(0 if self.persistent else self.max_iter):
             self._advance(it)
             if self.check_every and (it + 1) % self.check_every == 0 and it + 1 < self.max_iter:
                 if not bool((self.n > 0).any()):        # every trial reached tol: stop enqueueing
@@ -375,11 +382,10 @@ def run_concurrent(bos, streams=None):
     trial by trial (tests/test_gpu_bo_loop.py::test_concurrent_groups_equal_one_batch). Returns one BOResult per batch."""
     if not bos:
         return []
-    dev = bos[0].grid.device
-    cur = torch.cuda.current_stream(dev)
+    curs = [torch.cuda.current_stream(bo.device) for bo in bos]     # batches may live on different GPUs
     if streams is None:
-        streams = [torch.cuda.Stream(dev) for _ in bos]
-    for s in streams:
+        streams = [torch.cuda.Stream(bo.device) for bo in bos]
+    for s, cur in zip(streams, curs):
         s.wait_stream(cur)                              # buffers were initialised on the caller's stream
     max_iter = max(bo.max_iter for bo in bos)
     check_every = min((bo.check_every for bo in bos if bo.check_every), default=0)
@@ -399,7 +405,7 @@ def run_concurrent(bos, streams=None):
             if not alive:
                 break
     out = []
-    for bo, s in zip(bos, streams):
+    for bo, s, cur in zip(bos, streams, curs):
         with torch.cuda.stream(s):
             out.append(bo._end())
         cur.wait_stream(s)

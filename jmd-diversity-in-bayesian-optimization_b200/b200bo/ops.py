@@ -287,6 +287,29 @@ def fp64_fma_peak_tflops(device=None, reps=8) -> float:
     return best
 
 
+def smem_lds_peak_gbs(device=None, reps=6) -> float:
+    """Measured shared-memory read bandwidth of the current GPU in GB/s (conflict-free LDS.64, one 1024-thread CTA per SM;
+    best of ``reps``, CUDA events): the roofline denominator of the persistent BO loop (csrc/bo_persist.cu)."""
+    lib = _lib.load()
+    dev = torch.device(device or "cuda")
+    with torch.cuda.device(dev):
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        blocks, iters = sms, 1 << 17
+        out = torch.empty(blocks * 1024, dtype=torch.float64, device=dev)
+        best = 0.0
+        for r in range(reps + 2):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            nbytes = lib.b200bo_smem_lds_probe(_ptr(out), blocks, iters, _stream())
+            e1.record()
+            e1.synchronize()
+            if nbytes <= 0:
+                raise _lib.B200boError("smem_lds_probe failed: " + lib.b200bo_last_error_string().decode())
+            if r >= 2:
+                best = max(best, nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    return best
+
+
 def simplex_noise(hseed: int, vecs, xy: torch.Tensor) -> torch.Tensor:
     """Raw 2-D simplex noise at xy (M,2) f64 for SimplexNoise(seed,2) with hashed seed / table given."""
     import ctypes

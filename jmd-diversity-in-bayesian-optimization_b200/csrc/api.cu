@@ -47,9 +47,38 @@ __global__ void __launch_bounds__(256) fp64_fma_probe_kernel(double* out, int it
   for (int i = 0; i < 8; ++i) s += acc[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+
+// Shared-memory read-bandwidth probe: 1024 threads per CTA, one CTA per SM, 8 independent conflict-free LDS.64 per
+// thread and iteration out of a 32 KB table. The roofline denominator of the persistent BO loop (csrc/bo_persist.cu),
+// whose hot loop is one 8-byte kernel-table look-up per (candidate, observation) pair.
+__global__ void __launch_bounds__(1024) smem_lds_probe_kernel(double* out, int iters) {
+  __shared__ double tab[4096];
+  for (int e = threadIdx.x; e < 4096; e += 1024) tab[e] = e * 1e-6;
+  __syncthreads();
+  double acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+  for (int it = 0; it < iters; ++it) {
+    const int base = (threadIdx.x + it * 32) & 511;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += tab[base + k * 512];
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += acc[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
 }  // namespace b200bo
 
 extern "C" {
+
+long long b200bo_smem_lds_probe(double* out, int blocks, int iters, void* stream) {
+  if (!out || blocks < 1 || iters < 1) return b200bo::arg_error("smem_lds_probe: bad arguments");
+  b200bo::smem_lds_probe_kernel<<<blocks, 1024, 0, b200bo::as_stream(stream)>>>(out, iters);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return -(long long)b200bo::cuda_status(e, "smem_lds_probe");
+  return (long long)blocks * 1024 * iters * 8 * 8;   // bytes read from shared memory
+}
 
 long long b200bo_fp64_fma_probe(double* out, int blocks, int iters, void* stream) {
   if (!out || blocks < 1 || iters < 1) return b200bo::arg_error("fp64_fma_probe: bad arguments");
