@@ -77,6 +77,29 @@ int b200bo_dpp_table(int Gx, int Gy, double h, double gamma, double* table, void
 int b200bo_dpp_logdet_score_lattice(const double* table, int Gx, int Gy, const int32_t* idx, long long N, int k,
                                     double* logdet, void* stream);
 
+/* ---- ranked-DPP ordering on the device (csrc/dpp_rank.cu) ---------------------------------------
+ * b200bo_dpp_rank replaces ind = np.argsort(scores); dist = superset[ind]; scores[ind] (Src/data_gen.py:409-415), made
+ * deterministic: ascending (score, set index) — a stable LSD radix sort on the order-preserving 64-bit image of the
+ * f64 scores (NaN last, -0 == +0). z (N) f64 in; pos (N,k) int32 pool indices of the sets; pool (pool_size,2) f64.
+ * Out (each may be NULL): z_sorted (N), order (N) int32 = the permutation, pos_sorted (N,k), dist (N,k,2) f64 = the
+ * sets' points in rank order. ws: >= b200bo_dpp_rank_workspace_bytes(N). */
+size_t b200bo_dpp_rank_workspace_bytes(long long N);
+int b200bo_dpp_rank(const double* z, long long N, const int32_t* pos, int k, const double* pool, int pool_size,
+                    double* z_sorted, int32_t* order, int32_t* pos_sorted, double* dist, void* ws, size_t ws_bytes,
+                    void* stream);
+/* compare_subDPP's rank, np.sum(scores < z) (data_gen.py:481): count (1) uint64 out. */
+int b200bo_dpp_count_less(const double* scores, long long N, double z, uint64_t* count, void* stream);
+/* sub_dpp_sample's np.setdiff1d(range(lo, hi), acquiredsets)[r] (data_gen.py:445-466): the r-th (0-based) rank of the
+ * window [lo, hi) not yet acquired; acquired_mask ((N+31)/32 words, bit = rank) is updated; loc (1) int32 out (-1: fewer
+ * than r+1 ranks left); set_out (k,2) f64 = that set's points (NULL to skip). r is the host Generator's draw. */
+int b200bo_dpp_window_pick(uint32_t* acquired_mask, long long N, int lo, int hi, int r, const int32_t* pos_sorted, int k,
+                           const double* pool, int pool_size, int32_t* loc, double* set_out, void* stream);
+/* gammacalc (data_gen.py:758-842) scores the same N sets under every gamma of its range: one launch, the squared
+ * distances computed once per set. gammas (n_gamma) f64 on the device; logdet (n_gamma, N) f64 out; k <= 12. Values are
+ * bit-identical to b200bo_dpp_logdet_score called once per gamma. */
+int b200bo_dpp_logdet_score_multigamma(const double* pool, int pool_size, const int32_t* idx, long long N, int k,
+                                       const double* gammas, int n_gamma, double* logdet, void* stream);
+
 /* mean / population-sd / z-scores of the scoring block of sub_dpp, data_gen.py:406-408.
  * stats (2) f64 out = {mean, sd}; z (N) f64 out; ws: >= b200bo_dpp_stats_workspace_bytes(N). */
 size_t b200bo_dpp_stats_workspace_bytes(long long N);

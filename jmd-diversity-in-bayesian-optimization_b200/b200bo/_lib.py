@@ -23,6 +23,11 @@ PROTOTYPES = {
     "b200bo_dpp_table": (c_int, [c_int, c_int, c_double, c_double, P, P]),
     "b200bo_dpp_logdet_score_lattice": (c_int, [P, c_int, c_int, P, c_longlong, c_int, P, P]),
     "b200bo_dpp_stats_workspace_bytes": (c_size_t, [c_longlong]),
+    "b200bo_dpp_rank_workspace_bytes": (c_size_t, [c_longlong]),
+    "b200bo_dpp_rank": (c_int, [P, c_longlong, P, c_int, P, c_int, P, P, P, P, P, c_size_t, P]),
+    "b200bo_dpp_count_less": (c_int, [P, c_longlong, c_double, P, P]),
+    "b200bo_dpp_window_pick": (c_int, [P, c_longlong, c_int, c_int, c_int, P, c_int, P, c_int, P, P, P]),
+    "b200bo_dpp_logdet_score_multigamma": (c_int, [P, c_int, P, c_longlong, c_int, P, c_int, P, P]),
     "b200bo_dpp_zscore": (c_int, [P, c_longlong, P, P, P, c_size_t, P]),
     "b200bo_unrank_u128": (c_int, [P, P, P, P, c_uint64, c_uint64, c_int, c_int, c_longlong, P, P]),
     "b200bo_mt_seeded_randbelow": (c_int, [P, c_longlong, c_uint64, c_uint64, P, P, P, P]),

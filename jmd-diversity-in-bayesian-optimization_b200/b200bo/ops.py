@@ -118,6 +118,66 @@ def dpp_zscore(logdet: torch.Tensor):
     return stats, z
 
 
+def dpp_rank(z: torch.Tensor, pos: torch.Tensor = None, pool: torch.Tensor = None, want_dist=True):
+    """Stable ascending rank order of the scores on the device (csrc/dpp_rank.cu radix sort; data_gen.py:409-415):
+    returns (z_sorted (N), order (N) int32, pos_sorted (N,k) | None, dist (N,k,2) | None). Ties keep set-index order,
+    NaN sorts last."""
+    lib = _lib.load()
+    _cu(z, torch.float64, "z")
+    N = z.numel()
+    dev = z.device
+    k = 1
+    if pos is not None:
+        _cu(pos, torch.int32, "pos")
+        k = pos.shape[1]
+    if pool is not None:
+        _cu(pool, torch.float64, "pool")
+    z_sorted = torch.empty(N, dtype=torch.float64, device=dev)
+    order = torch.empty(N, dtype=torch.int32, device=dev)
+    pos_sorted = torch.empty((N, k), dtype=torch.int32, device=dev) if pos is not None else None
+    dist = torch.empty((N, k, 2), dtype=torch.float64, device=dev) if (pos is not None and pool is not None and want_dist) else None
+    wsb = int(lib.b200bo_dpp_rank_workspace_bytes(N))
+    ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device=dev)
+    check(lib.b200bo_dpp_rank(_ptr(z), N, _ptr(pos), k, _ptr(pool), 0 if pool is None else pool.shape[0], _ptr(z_sorted),
+                              _ptr(order), _ptr(pos_sorted), _ptr(dist), _ptr(ws), ws.numel(), _stream()), "dpp_rank")
+    return z_sorted, order, pos_sorted, dist
+
+
+def dpp_count_less(scores: torch.Tensor, z: float) -> int:
+    """np.sum(scores < z) on the device (compare_subDPP, data_gen.py:481). One device -> host read of 8 bytes."""
+    lib = _lib.load()
+    _cu(scores, torch.float64, "scores")
+    out = torch.empty(1, dtype=torch.int64, device=scores.device)
+    check(lib.b200bo_dpp_count_less(_ptr(scores), scores.numel(), float(z), _ptr(out), _stream()), "dpp_count_less")
+    return int(out.item())
+
+
+def dpp_window_pick(acquired_mask: torch.Tensor, N: int, lo: int, hi: int, r: int, pos_sorted: torch.Tensor, pool: torch.Tensor):
+    """The r-th not-yet-acquired rank of [lo, hi) (marked in acquired_mask, int32 words) and that set's points:
+    returns (loc int, set (k,2) f64 host array) — sub_dpp_sample's setdiff1d + look-up (data_gen.py:445-466)."""
+    lib = _lib.load()
+    _cu(acquired_mask, torch.int32, "acquired_mask"); _cu(pos_sorted, torch.int32, "pos_sorted"); _cu(pool, torch.float64, "pool")
+    k = pos_sorted.shape[1]
+    out = torch.empty(2 * k + 1, dtype=torch.float64, device=pool.device)       # [set (k,2) | loc as int32 bits]
+    loc_view = out[2 * k:].view(torch.int32)
+    check(lib.b200bo_dpp_window_pick(_ptr(acquired_mask), int(N), int(lo), int(hi), int(r), _ptr(pos_sorted), k, _ptr(pool),
+                                     pool.shape[0], _ptr(loc_view), _ptr(out), _stream()), "dpp_window_pick")
+    host = out.cpu()
+    return int(host[2 * k:].view(torch.int32)[0]), host[:2 * k].reshape(k, 2).numpy()
+
+
+def dpp_logdet_score_multigamma(pool: torch.Tensor, idx: torch.Tensor, gammas) -> torch.Tensor:
+    """(n_gamma, N) f64 log-dets of the same N sets under every gamma in one launch (gammacalc, data_gen.py:758-842)."""
+    lib = _lib.load()
+    _cu(pool, torch.float64, "pool"); _cu(idx, torch.int32, "idx")
+    g = torch.as_tensor(gammas, dtype=torch.float64, device=pool.device).contiguous()
+    N, k = idx.shape
+    out = torch.empty((g.numel(), N), dtype=torch.float64, device=pool.device)
+    check(lib.b200bo_dpp_logdet_score_multigamma(_ptr(pool), pool.shape[0], _ptr(idx), N, k, _ptr(g), g.numel(), _ptr(out),
+                                                 _stream()), "dpp_logdet_score_multigamma")
+    return out
+
+
 _BINOM_CACHE = {}
 
 

@@ -56,6 +56,8 @@ class diverse_data_generator:
         self._lat = None
         self._lat_key = None
         self._tables = {}
+        self._pos = self._pos_sorted = self._scores_dev = self._acq_mask = None
+        self._acq_seen = 0
 
     # ------------------------------------------------------------------ bookkeeping (data_gen.py:110-171)
     @property
@@ -187,10 +189,11 @@ class diverse_data_generator:
         if self.training_size > 1:
             logdet = self.score_sets(pos)
             stats, z = ops.dpp_zscore(logdet)
-            z_sorted, ind = torch.sort(z, stable=True)       # ascending (score, set index): data_gen.py:409 made deterministic
-            dist = pool[pos.long()[ind]]
+            # ascending (score, set index): data_gen.py:409 made deterministic — device radix sort + gather
+            z_sorted, _, self._pos_sorted, dist = ops.dpp_rank(z, pos, pool)
             self.mean, self.sd = (float(v) for v in stats.cpu())
-            self._pos_sorted = pos[ind]
+            self._pos, self._scores_dev = pos, z_sorted
+            self._acq_mask, self._acq_seen = None, 0
             self.data[self.key].update({"scores": z_sorted.cpu().numpy(), "dist": dist.cpu().numpy()})
             self.update_data_dict()
         else:
@@ -215,16 +218,34 @@ class diverse_data_generator:
             return int(95 / 100 * n), n
         return 0, int(5 / 100 * n)
 
+    def _acquired_mask(self):
+        """Device bit mask of self.acquiredsets (bit = rank), rebuilt whenever the public list was changed from outside."""
+        n = self.options["N_samples"]
+        if self._acq_mask is None or self._acq_seen != len(self.acquiredsets) or self._acq_mask.numel() != (n + 31) // 32:
+            words = np.zeros((n + 31) // 32, dtype=np.uint32)
+            for loc in self.acquiredsets:
+                words[int(loc) >> 5] |= np.uint32(1) << np.uint32(int(loc) & 31)
+            self._acq_mask = torch.as_tensor(words.view(np.int32), device=self.device)
+            self._acq_seen = len(self.acquiredsets)
+        return self._acq_mask
+
     def _pick(self, percentile):
+        """One draw from a percentile's rank window minus the acquired ranks (data_gen.py:445-466). The reference draws
+        Generator.choice(list(possible), 1) over possible = np.setdiff1d(window, acquiredsets): that is possible[r] with
+        r the Generator's draw from range(len(possible)) — same stream position, same r; the r-th free rank of the window
+        and its set are found on the device (csrc/dpp_rank.cu:window_pick_kernel)."""
         lo, hi = self._window(percentile, self.options["N_samples"])
-        possible = np.setdiff1d(list(range(lo, hi)), self.acquiredsets)
+        free = (hi - lo) - len({int(a) for a in self.acquiredsets if lo <= a < hi})
         try:
-            loc = self.rng["sampler"].choice(list(possible), 1)[0]
+            r = int(self.rng["sampler"].choice(free, 1)[0])
         except ValueError:
             raise Exception("Constructed batch-DPP space exhausted above its {}th percentile. Re-generate the distribution "
                             "or sample from a smaller percentile.".format(percentile))
+        loc, pts = ops.dpp_window_pick(self._acquired_mask(), self.options["N_samples"], lo, hi, r, self._pos_sorted,
+                                       self._pool_device())
         self.acquiredsets.append(loc)
-        return loc
+        self._acq_seen += 1
+        return loc, pts
 
     def sub_dpp_sample(self, percentiles):
         try:
@@ -232,9 +253,8 @@ class diverse_data_generator:
         except Exception:
             raise Exception("Data needs to be generated first using the generator method")
         if isinstance(percentiles, (list, np.ndarray)):
-            locs = [self._pick(p) for p in percentiles]
-            return self.data[self.key]["dist"][locs]
-        return self.data[self.key]["dist"][self._pick(percentiles)]
+            return np.stack([self._pick(p)[1] for p in percentiles])
+        return self._pick(percentiles)[1]
 
     # ------------------------------------------------------------------ scoring API (data_gen.py:472-497)
     def twoD_score(self, subset, gamma):
@@ -256,7 +276,11 @@ class diverse_data_generator:
         d = self.data[resultkey]
         score = self.twoD_score(subset, d["gamma"])
         z = (score - d["mean"]) / d["standard-deviation"]
-        return int(np.sum(d["scores"] < z)), z
+        if resultkey == self.key and getattr(self, "_scores_dev", None) is not None:
+            scores = self._scores_dev                                     # still resident from generate()
+        else:
+            scores = torch.as_tensor(np.ascontiguousarray(d["scores"], dtype=np.float64), device=self.device)
+        return ops.dpp_count_less(scores, z), z
 
     # ------------------------------------------------------------------ gamma selection (data_gen.py:758-842)
     def gammacorrelation(self, g1, g2, min_samples):
@@ -274,6 +298,40 @@ class diverse_data_generator:
             np.random.shuffle(y)
         return scipy.stats.linregress(x, y).rvalue
 
+    def _gamma_scores(self, exponents, min_samples):
+        """What the 256 gammacorrelation calls of gammacalc recompute, once: the SAME min_samples sets (generate() with a
+        fixed seed draws identical sets whatever gamma is) scored under every gamma of the range in one launch
+        (csrc/dpp_rank.cu:dpp_multigamma_kernel), then per gamma the z-scores and the stable rank order on the device.
+        Returns (raw (n_gamma, N) host log-dets, per-gamma sorted z-scores, per-gamma order)."""
+        import scipy.stats  # noqa: F401  (linregress, used by the caller)
+        self.options["N_samples"] = min_samples
+        self.options["parallel-process"] = False
+        self.gamma = 10.0 ** exponents[0]
+        self.generate()
+        pos, pool = self._pos, self._pool_device()
+        raw = ops.dpp_logdet_score_multigamma(pool, pos, [10.0 ** g for g in exponents])
+        zs, orders = [], []
+        for row in raw:
+            _, z = ops.dpp_zscore(row.contiguous())
+            z_sorted, order, _, _ = ops.dpp_rank(z)
+            zs.append(z_sorted.cpu().numpy())
+            orders.append(order.cpu().numpy())
+        self.gamma = 10.0 ** exponents[-1]                       # where the reference's last gammacorrelation leaves it
+        return raw.cpu().numpy(), zs, orders
+
+    @staticmethod
+    def _gammacorrelation_batched(batched, i, j):
+        """gammacorrelation(g_i, g_j) (data_gen.py:758-779) from the batched scores: same host arithmetic as there."""
+        import scipy.stats
+        raw, zs, orders = batched
+        score1 = zs[i]
+        s2 = raw[j][orders[i]]
+        s2 = (s2 - s2.mean()) / np.std(s2)
+        x, y = np.argsort(score1), np.argsort(s2)
+        if np.isnan(s2).any():
+            np.random.shuffle(y)
+        return scipy.stats.linregress(x, y).rvalue
+
     def gammacalc(self, grange=None, plot=False, annotations=False, min_samples=200):
         if plot:
             raise NotImplementedError("plotting is outside the hot path")
@@ -281,12 +339,15 @@ class diverse_data_generator:
         if self.gamma_correlation_dict is None:
             self.gamma_correlation_dict = {}
         m = np.zeros((len(gamma_range), len(gamma_range)))
+        batched = None
         for i, g1 in enumerate(gamma_range):
             for j, g2 in enumerate(gamma_range):
                 try:
                     m[i, j] = self.gamma_correlation_dict[g1][g2]
                 except KeyError:
-                    m[i, j] = self.gammacorrelation(g1, g2, min_samples)
+                    if batched is None:
+                        batched = self._gamma_scores(list(gamma_range), min_samples)
+                    m[i, j] = self._gammacorrelation_batched(batched, i, j)
                     self.gamma_correlation_dict.setdefault(g1, {})[g2] = m[i, j]
                     self.gamma_correlation_dict.setdefault(g2, {})[g1] = m[i, j]
         np.fill_diagonal(m, 0)

@@ -264,3 +264,87 @@ def test_nearly_singular_sets_keep_their_ranking_information(lattice_grid):
     both = np.isfinite(got) & np.isfinite(ref)              # LAPACK's pivoted LU meets an exactly-zero pivot on a few sets
     assert np.all(~np.isnan(got)) and both.mean() > 0.95
     assert scipy.stats.spearmanr(got[both], ref[both])[0] > 0.8
+
+
+DEV = "cuda:0"
+
+
+# ---- device ordering: radix sort / gather / rank / window pick / multi-gamma (csrc/dpp_rank.cu) ------------------------
+
+@pytest.mark.parametrize("N", [1, 5, 255, 2047, 2048, 2049, 100003])
+def test_device_rank_is_the_stable_ascending_order(N):
+    """b200bo_dpp_rank == np.argsort(kind='stable') on the scores (ties by set index, NaN last, -0 == +0) and the gathered
+    z / index sets / point sets equal fancy indexing (Src/data_gen.py:409-415)."""
+    from b200bo import ops
+    rng = np.random.default_rng(N)
+    z = rng.normal(size=N)
+    if N > 4:
+        z[rng.integers(0, N, N // 3)] = np.round(z[rng.integers(0, N, N // 3)], 1)      # many exact ties
+        z[rng.integers(0, N, 3)] = np.nan
+        z[rng.integers(0, N, 2)] = -0.0
+        z[rng.integers(0, N, 2)] = 0.0
+        z[rng.integers(0, N, 2)] = np.inf
+        z[rng.integers(0, N, 2)] = -np.inf
+        z[rng.integers(0, N, 2)] = 5e-324
+        z[rng.integers(0, N, 2)] = -5e-324
+    k = 10
+    pos = rng.integers(0, 10000, size=(N, k)).astype(np.int32)
+    ax = np.arange(0, 100, 1.0)
+    pool = np.stack(np.meshgrid(ax, ax), axis=-1).reshape(-1, 2)
+    t = lambda a: torch.as_tensor(a, device=DEV)
+    zs, order, ps, dist = ops.dpp_rank(t(z), t(pos), t(pool))
+    ref = np.argsort(z, kind="stable")
+    assert np.array_equal(order.cpu().numpy(), ref)
+    assert np.array_equal(zs.cpu().numpy(), z[ref], equal_nan=True)
+    assert np.array_equal(ps.cpu().numpy(), pos[ref])
+    assert np.array_equal(dist.cpu().numpy(), pool[pos[ref]])
+    zs2, order2, ps2, dist2 = ops.dpp_rank(t(z))                        # scores only
+    assert ps2 is None and dist2 is None and np.array_equal(order2.cpu().numpy(), ref)
+
+
+def test_device_count_less_and_window_pick_equal_numpy():
+    """compare_subDPP's np.sum(scores < z) and sub_dpp_sample's np.setdiff1d(range(lo, hi), acquired)[r] with the set
+    look-up (Src/data_gen.py:445-466,481), windows cut at / off 32-bit word boundaries, ranks acquired one by one."""
+    from b200bo import ops
+    rng = np.random.default_rng(4)
+    N, k = 10000, 10
+    scores = np.sort(rng.normal(size=N))
+    for zq in (-10.0, scores[17], scores[5000], 0.123, 10.0, np.nan):
+        assert ops.dpp_count_less(torch.as_tensor(scores, device=DEV), zq) == int(np.sum(scores < zq))
+    ax = np.arange(0, 100, 1.0)
+    pool = np.stack(np.meshgrid(ax, ax), axis=-1).reshape(-1, 2)
+    pos_sorted = rng.integers(0, 10000, size=(N, k)).astype(np.int32)
+    mask = torch.zeros((N + 31) // 32, dtype=torch.int32, device=DEV)
+    acquired = []
+    tp, tpool = torch.as_tensor(pos_sorted, device=DEV), torch.as_tensor(pool, device=DEV)
+    for lo, hi in [(0, 500), (250, 500), (9500, 10000), (31, 33), (64, 96), (4999, 5001), (0, 10000)]:
+        for _ in range(12):
+            possible = np.setdiff1d(np.arange(lo, hi), acquired)
+            if len(possible) == 0:
+                break
+            r = int(rng.integers(0, len(possible)))
+            loc, pts = ops.dpp_window_pick(mask, N, lo, hi, r, tp, tpool)
+            assert loc == possible[r], (lo, hi, r, loc, possible[r])
+            assert np.array_equal(pts, pool[pos_sorted[loc]])
+            acquired.append(loc)
+        possible = np.setdiff1d(np.arange(lo, hi), acquired)
+        loc, _ = ops.dpp_window_pick(mask, N, lo, hi, len(possible), tp, tpool)      # one past the last free rank
+        assert loc == -1
+    words = np.zeros((N + 31) // 32, dtype=np.uint32)
+    for a in acquired:
+        words[a >> 5] |= np.uint32(1) << np.uint32(a & 31)
+    assert np.array_equal(mask.cpu().numpy().view(np.uint32), words)
+
+
+@pytest.mark.parametrize("k", [2, 5, 10, 12])
+def test_multigamma_scores_are_bit_identical_to_one_launch_per_gamma(k):
+    from b200bo import ops
+    rng = np.random.default_rng(k)
+    ax = np.arange(0, 100, 1.0)
+    pool = torch.as_tensor(np.stack(np.meshgrid(ax, ax), axis=-1).reshape(-1, 2), device=DEV)
+    idx = torch.as_tensor(np.stack([rng.choice(10000, k, replace=False) for _ in range(777)]).astype(np.int32), device=DEV)
+    gammas = [10.0 ** e for e in range(-12, 4)]
+    multi = ops.dpp_logdet_score_multigamma(pool, idx, gammas)
+    assert multi.shape == (16, 777)
+    for i, g in enumerate(gammas):
+        assert torch.equal(multi[i], ops.dpp_logdet_score(pool, idx, g)), g
