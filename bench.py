@@ -616,26 +616,72 @@ def bench_dpp(dev):
         out[name] = {"sets": int(t.shape[0]), "ms": ms, "sets_per_s": t.shape[0] / (ms * 1e-3)}
     out["lattice_identical_to_generic"] = bool(torch.equal(ops.dpp_logdet_score_lattice(lat, table, idx),
                                                            ops.dpp_logdet_score(pool, idx, 1e-5)))
-    # end to end at config-2 size: score + mean/std/z-score + stable sort + gather of the sorted sets
-    def e2e():
-        ld = ops.dpp_logdet_score(pool, idx, 1e-5)
+    # end to end at config-2 size: score + mean/std/z-score + device radix sort + gather of the sorted sets (csrc/dpp_rank.cu)
+    def ev(fn, reps=5, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps
+
+    def rank_dev():
+        ld = ops.dpp_logdet_score_lattice(lat, table, idx)
+        stats, z = ops.dpp_zscore(ld)
+        return ops.dpp_rank(z, idx, pool)
+
+    def rank_torch():
+        ld = ops.dpp_logdet_score_lattice(lat, table, idx)
         stats, z = ops.dpp_zscore(ld)
         zs, order = torch.sort(z, stable=True)
-        return pool[idx.long()[order]]
-    for _ in range(3):
-        e2e()
-    torch.cuda.synchronize(dev)
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5):
-        e2e()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1) / 5
-    out["rank_n1e5"] = {"sets": 100000, "ms": ms, "sets_per_s": 1e5 / (ms * 1e-3), "what": "score + z-score + stable sort + gather"}
-    # FP64-pipe accounting of the scorer (k = 10): 45 pairs x (exp 22 + sqrt 15 + 8) + Cholesky 220 FMA + 10 x (sqrt 15 +
-    # div 14) + 10 x log 51 ~ 3045 DFMA-slots per set (profiles/fp64_peaks_r1.json slot costs)
-    out["fp64_pipe_frac_n1e7"] = out["n1e7"]["sets_per_s"] * 3045 * 2 / 1e12 / 36.6
+        return zs, order, idx[order], pool[idx.long()[order]]
+
+    ms = ev(rank_dev)
+    ms_t = ev(rank_torch)
+    a, b = rank_dev(), rank_torch()
+    out["rank_n1e5"] = {"sets": 100000, "ms": ms, "sets_per_s": 1e5 / (ms * 1e-3),
+                        "what": "score (lattice table) + z-score + hand-written stable radix sort + gather of the sorted sets",
+                        "ms_with_torch_sort_and_indexing": ms_t,
+                        "same_order_as_torch_stable_sort": bool(torch.equal(a[1].long(), b[1]))}
+    z1 = ops.dpp_zscore(ops.dpp_logdet_score_lattice(lat, table, idx))[1]
+    zbig = ops.dpp_zscore(ops.dpp_logdet_score_lattice(lat, table, big))[1]
+    out["sort_only"] = {"n1e5_ms": ev(lambda: ops.dpp_rank(z1)), "n1e5_torch_ms": ev(lambda: torch.sort(z1, stable=True)),
+                        "n1e7_ms": ev(lambda: ops.dpp_rank(zbig), reps=3, warm=1),
+                        "n1e7_torch_ms": ev(lambda: torch.sort(zbig, stable=True), reps=3, warm=1),
+                        "what": "b200bo_dpp_rank on the z-scores alone (8 x 8-bit stable LSD passes) beside torch.sort(stable=True)"}
+    # end to end with HOST buffers: pinned index sets in, sorted z-scores + permutation out (config 2 through the C ABI)
+    idx_h = idx.cpu().pin_memory()
+    zs_h = torch.empty(100000, dtype=torch.float64).pin_memory()
+    ord_h = torch.empty(100000, dtype=torch.int32).pin_memory()
+
+    def e2e_host():
+        d = idx_h.to(dev, non_blocking=True)
+        ld = ops.dpp_logdet_score_lattice(lat, table, d)
+        stats, z = ops.dpp_zscore(ld)
+        zs, order, _, _ = ops.dpp_rank(z)
+        zs_h.copy_(zs, non_blocking=True); ord_h.copy_(order, non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    ms = ev(e2e_host)
+    out["e2e_host_n1e5"] = {"sets": 100000, "ms": ms, "sets_per_s": 1e5 / (ms * 1e-3), "h2d_bytes": 4000000, "d2h_bytes": 1200000,
+                            "what": "pinned (N,10) int32 index sets -> device -> score + z-score + rank -> sorted scores and "
+                                    "permutation back on the host"}
+    # roofline of the scorer by SURVEY.md 8(d): 623 flops per set (k = 10; exp / log / sqrt / div = 1 flop) against the
+    # FP64 pipe; the slot view counts what the pipe really issues (exp 22, sqrt 15, div 14, log 51 DFMA-slots:
+    # profiles/fp64_peaks_r1.json), i.e. 3045 slots per set for the generic kernel and 870 for the lattice-table variant
+    peak = 37.055
+    out["roofline"] = {"bound": "fp64 pipe", "flops_per_set": 623, "peak_tflops": peak,
+                       "generic": {"achieved_tflops": out["n1e7"]["sets_per_s"] * 623 / 1e12,
+                                   "frac": out["n1e7"]["sets_per_s"] * 623 / 1e12 / peak,
+                                   "pipe_slot_frac": out["n1e7"]["sets_per_s"] * 3045 * 2 / 1e12 / peak},
+                       "lattice": {"achieved_tflops": out["lattice_n1e7"]["sets_per_s"] * 623 / 1e12,
+                                   "frac": out["lattice_n1e7"]["sets_per_s"] * 623 / 1e12 / peak,
+                                   "pipe_slot_frac": out["lattice_n1e7"]["sets_per_s"] * 870 * 2 / 1e12 / peak},
+                       "hbm_bytes_per_set": 48, "hbm_gbs_lattice": out["lattice_n1e7"]["sets_per_s"] * 48 / 1e9}
     # the reference's generate() path (un-rank + score + rank) at its own size, N = 10 000 (3.22 s in SURVEY.md §6)
     import data_gen
     d = data_gen.diverse_data_generator()
@@ -653,6 +699,20 @@ def bench_dpp(dev):
                             "note": "per-element seeds from numpy's legacy generator on the host (as data_gen.py:866-867); the "
                                     "seeded Mersenne-Twister randint per element (csrc/mt_rank.cu, bit-exact vs CPython), "
                                     "un-ranking, scoring, statistics and the sort run on the GPU; reference: 3.22 s (SURVEY.md 6)"}
+    # gammacalc (data_gen.py:758-842; 15.6 s in the reference): 16 gammas x 200 sets, one multi-gamma launch
+    d2 = data_gen.diverse_data_generator()
+    d2.device = str(dev)
+    d2.options["bounds"] = [(0, 100), (0, 100)]
+    d2.options["seed"] = 0
+    d2.training_size = 10
+    d2.gammacalc(grange=(-6, 1))                                    # warm-up on a short range
+    d2.gamma_correlation_dict = {}
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    pair = d2.gammacalc()
+    torch.cuda.synchronize(dev)
+    out["gammacalc_16x16_n200"] = {"seconds": time.perf_counter() - t0, "pair": [int(v) for v in pair] if pair is not None else None,
+                                   "reference_seconds": 15.6, "note": "wall clock incl. the 136 host-side rank regressions"}
     # CPU: the oracle's twoD_score restatement (numpy slogdet), one core, bounded sample
     from oracle import dpp as odpp
     pool_h = pool.cpu().numpy()

@@ -14,7 +14,8 @@ tests or golden vectors for it.  Anchors are the reference's call sites:
 * fit                      BO.py:144,189 (fit_gpytorch_model -> scipy L-BFGS-B)
 
 and the published formulas.  An independent check
-against scikit-learn's exact GP is in tests/test_oracle_golden.py.
+against scikit-learn's exact GP is in tests/test_oracle_golden.py; mpmath (EI tails), torch autograd
+of an independent MLL formulation and the explicit-inverse posterior are in tests/test_oracle_pin.py.
 
 Conventions shared with the CUDA kernels (include/b200bo.h):
   theta = (noise sigma^2, constant c, outputscale s, lengthscale l)  — *actual* values
