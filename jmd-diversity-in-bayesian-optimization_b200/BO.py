@@ -12,7 +12,12 @@ Deliberate differences from the reference as written, all
   coded it falls back to gpytorch defaults after the first model re-creation, BO.py:424-429);
   ``reference_quirk=True`` reproduces the as-coded behaviour;
 * candidates that coincide with an observation are masked instead of being jittered (BO.py:90-92);
-* numerical failures are per-trial status bits, not exceptions with roll-back (BO.py:187-239).
+* numerical failures are per-trial status bits, not exceptions with roll-back (BO.py:187-239);
+* ``minstate=True`` (the objective is passed negated, Optimizers.py:48-52): the reference seeds ``yopt`` / ``yall[0]``
+  and the first EI's ``best_f`` with ``train_obj.min()`` of the NEGATED values, i.e. the worst initial point
+  (BO.py:27-28,141,146); here the incumbent is the best initial point from the start (max of the negated values), as
+  it is from the second iteration on in the reference too (``train_obj_ei.max()``, BO.py:168). ``generate_initial_data``
+  itself still returns the reference's value. The Wildcat Wells experiments all maximise.
 """
 import random
 

@@ -483,7 +483,7 @@ bo_fixed_loop_kernel(const BoPersistParams p) {
 __global__ void __launch_bounds__(256)
 kernel_table_ysigned_kernel(const double* __restrict__ theta, int kernel_id, double h, int Gx, int Gy,
                             double* __restrict__ ktabY) {
-  const int slot = blockIdx.y;
+  const int slot = blockIdx.y;                                       // H <= 65535 (checked by the entry)
   const double sc = theta[(size_t)slot * 4 + 2], ell = theta[(size_t)slot * 4 + 3];
   const KernParams kp = make_kern_params(sc, ell, kernel_id);
   const int H2 = 2 * Gy - 1;

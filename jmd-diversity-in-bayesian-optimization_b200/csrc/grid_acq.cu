@@ -1080,14 +1080,15 @@ static int dispatch_ni(const GridAcqParams& p, int T, cudaStream_t st) {
 __global__ void __launch_bounds__(256)
 kernel_table_kernel(const double* __restrict__ theta, int H, int kernel_id, double h, int TW, int TH,
                     double* __restrict__ ktab) {
-  const int slot = blockIdx.y;
-  const double sc = theta[(size_t)slot * 4 + 2], ell = theta[(size_t)slot * 4 + 3];
-  const KernParams kp = make_kern_params(sc, ell, kernel_id);
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < TW * TH; e += gridDim.x * blockDim.x) {
-    const int dyi = e / TW, dxi = e - dyi * TW;
-    const double dx = h * (double)dxi, dy = h * (double)dyi;
-    const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-    ktab[(size_t)slot * TW * TH + e] = kernel_from_r2_dyn(kernel_id, r2, sc, ell, kp.a_scale);
+  for (int slot = blockIdx.y; slot < H; slot += gridDim.y) {         // gridDim.y <= 65535: slots beyond that wrap
+    const double sc = theta[(size_t)slot * 4 + 2], ell = theta[(size_t)slot * 4 + 3];
+    const KernParams kp = make_kern_params(sc, ell, kernel_id);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < TW * TH; e += gridDim.x * blockDim.x) {
+      const int dyi = e / TW, dxi = e - dyi * TW;
+      const double dx = h * (double)dxi, dy = h * (double)dyi;
+      const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+      ktab[(size_t)slot * TW * TH + e] = kernel_from_r2_dyn(kernel_id, r2, sc, ell, kp.a_scale);
+    }
   }
 }
 
@@ -1138,14 +1139,14 @@ static int grid_acq_common(bool lattice, const double* grid, int G, int Gx, int 
   p.var_floor = var_floor;
   p.n_cap = (n_hint > 0 && n_hint < n_max) ? n_hint : n_max;
   p.chunks = pick_chunks(T, G, 148 * kb_ctas_per_sm(lattice, p.n_cap));
-  p.prune = env_int("B200BO_KB_PRUNE", 1);
+  static const int prune_env = env_int("B200BO_KB_PRUNE", 1);   // read once per process
+  p.prune = prune_env;
   p.cols_per_cta = (((G + p.chunks - 1) / p.chunks + GA_THREADS - 1) / GA_THREADS) * GA_THREADS;
   p.part_val = reinterpret_cast<double*>(ws);
   p.part_idx = reinterpret_cast<int32_t*>(p.part_val + (size_t)T * p.chunks);
   p.mu_out = mu; p.var_out = var; p.acq_out = acq;
   p.status = status;
   p.n_max = n_max;
-  p.n_cap = (n_hint > 0 && n_hint < n_max) ? n_hint : n_max;
   p.wstride = b200bo_wfrag_doubles(n_max);
   p.Gx = Gx; p.Gy = Gy; p.x0 = x0; p.y0 = y0; p.h = h; p.ktab = ktab; p.ktab_id = ktab_id;
   int rc;
@@ -1194,9 +1195,9 @@ int b200bo_grid_posterior_acq_argmax_lattice(int Gx, int Gy, double x0, double y
 int b200bo_kernel_table(const double* theta, int H, int kernel_id, double h, int TW, int TH, double* ktab, void* stream) {
   using namespace b200bo;
   if (!theta || !ktab) return arg_error("kernel_table: null pointer");
-  if (H < 1 || TW < 1 || TH < 1 || !(h > 0.0) || H > 65535) return arg_error("kernel_table: bad sizes H=%d TW=%d TH=%d", H, TW, TH);
+  if (H < 1 || TW < 1 || TH < 1 || !(h > 0.0)) return arg_error("kernel_table: bad sizes H=%d TW=%d TH=%d", H, TW, TH);
   if (kernel_id < 0 || kernel_id > 3) return arg_error("kernel_table: kernel_id=%d", kernel_id);
-  dim3 grid((TW * TH + 255) / 256 > 64 ? 64 : (TW * TH + 255) / 256, H);
+  dim3 grid((TW * TH + 255) / 256 > 64 ? 64 : (TW * TH + 255) / 256, H > 65535 ? 65535 : H);
   kernel_table_kernel<<<grid, 256, 0, as_stream(stream)>>>(theta, H, kernel_id, h, TW, TH, ktab);
   B200BO_CHECK_LAUNCH("kernel_table");
   return 0;

@@ -247,8 +247,8 @@ int b200bo_grid_posterior_update_acq_argmax(int Gx, int Gy, double x0, double y0
   p.part_val = reinterpret_cast<double*>(ws);
   p.part_idx = ws ? reinterpret_cast<int32_t*>(p.part_val + (size_t)T * p.chunks) : nullptr;
   p.acq_out = acq; p.status = status; p.n_max = n_max;
-  const char* pr = getenv("B200BO_KB_PRUNE");
-  p.prune = pr ? atoi(pr) : 1;
+  static const int prune_env = [] { const char* pr = getenv("B200BO_KB_PRUNE"); return pr ? atoi(pr) : 1; }();
+  p.prune = prune_env;
   size_t smem = (size_t)n_max * (sizeof(double) + sizeof(int));
   grid_inc_kernel<<<(unsigned)((size_t)T * p.chunks), GI_THREADS, smem, st>>>(p);
   B200BO_CHECK_LAUNCH(who);
