@@ -239,7 +239,10 @@ int b200bo_grid_posterior_update_acq_argmax(int Gx, int Gy, double x0, double y0
  * iteration. Same posterior recurrences as those entries (rank-1 row of L^-1, per-candidate (mu - c, s - var) folded
  * row by row); the kernel table lives in shared memory, the per-candidate state in a per-CTA scratch (L2-resident).
  * ktabY (H, 2Gy-1, Gx) f64 from b200bo_kernel_table_ysigned: ktabY[slot][(dy + Gy-1) Gx + |dx|]; ktab_id (T) or NULL;
- * order (T) int32 processing order (e.g. trials sorted by slot, so a CTA reloads its table rarely) or NULL.
+ * H = number of table slots; for H > 1: order (T) int32 = the trials sorted by slot and slot_start (H+1) int32 = first
+ * position of every slot in order (all three may be NULL for H == 1). Two kernel variants, chosen by what fits: two
+ * trials per CTA (two 512-thread halves on ONE unsigned table, 80 KB for 100 x 100: the latency-bound phases of one
+ * trial overlap the look-up loop of the other; B200BO_KF_DUAL=0 disables it) or one trial per CTA on the y-signed table.
  * In: X (T,n_max,2), y (T,n_max), n (T) = initial observations (>= 1). Out: X, y, n (observations at the end, positive),
  * best_f (T), yall (T,max_iter+2) padded as BO.py:262-271, picked (T,max_iter) (-1 = none), nit (T), status (T).
  * A trial whose start is off the lattice or whose appended pivot is not positive comes back with
@@ -253,10 +256,10 @@ int b200bo_bo_fixed_loop_supported(int Gx, int Gy, int n_max);
 int b200bo_bo_fixed_loop_ctas(int T);
 size_t b200bo_bo_fixed_loop_workspace_bytes(int T, int Gx, int Gy);
 int b200bo_bo_fixed_loop(int Gx, int Gy, double x0, double y0, double h, const double* ktabY, const int32_t* ktab_id,
-                         const int32_t* order, const float* obj, const int32_t* surf_id, double* X, double* y, int32_t* n,
-                         const double* theta, double* best_f, double* yall, int32_t* picked, int32_t* nit,
-                         int32_t* status, int T, int n_max, int max_iter, int acq_id, double acq_param, double var_floor,
-                         double tol, double optimal_y, void* ws, size_t ws_bytes, void* stream);
+                         const int32_t* order, const int32_t* slot_start, int H, const float* obj, const int32_t* surf_id,
+                         double* X, double* y, int32_t* n, const double* theta, double* best_f, double* yall, int32_t* picked,
+                         int32_t* nit, int32_t* status, int T, int n_max, int max_iter, int acq_id, double acq_param,
+                         double var_floor, double tol, double optimal_y, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- K-C  marginal log-likelihood value and gradient ----------------------------
  * replaces ExactMarginalLogLikelihood + autograd inside fit_gpytorch_model (BO.py:144,189).

@@ -57,9 +57,9 @@ PROTOTYPES = {
     "b200bo_bo_fixed_loop_supported": (c_int, [c_int, c_int, c_int]),
     "b200bo_bo_fixed_loop_ctas": (c_int, [c_int]),
     "b200bo_bo_fixed_loop_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "b200bo_bo_fixed_loop": (c_int, [c_int, c_int, c_double, c_double, c_double, P, P, P, P, P, P, P, P, P, P, P, P, P,
-                                     P, c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_double, P, c_size_t,
-                                     P]),
+    "b200bo_bo_fixed_loop": (c_int, [c_int, c_int, c_double, c_double, c_double, P, P, P, P, c_int, P, P, P, P, P, P, P, P,
+                                     P, P, P, c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_double, P,
+                                     c_size_t, P]),
     "b200bo_mll_value_grad": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "b200bo_lbfgs_state_bytes": (c_size_t, [c_int]),
     "b200bo_lbfgs_init": (c_int, [P, P, P, c_int, P, P, c_int, c_double, P]),

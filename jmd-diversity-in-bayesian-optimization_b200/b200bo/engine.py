@@ -133,7 +133,11 @@ class BatchedBO:
             self.ktabY = ops.kernel_table_ysigned(uniq.contiguous(), self.kernel_id, self.lattice)
             self.ktab_id = inv.to(i32).contiguous()
             # trials that share a table run back to back on a CTA (the table is reloaded only when the slot changes)
-            self.order = (torch.sort(self.ktab_id, stable=True)[1].to(i32).contiguous() if uniq.shape[0] > 1 else None)
+            self.order = self.slot_start = None
+            if uniq.shape[0] > 1:
+                self.order = torch.sort(self.ktab_id, stable=True)[1].to(i32).contiguous()
+                counts = torch.bincount(self.ktab_id.long(), minlength=uniq.shape[0])
+                self.slot_start = torch.cat([counts.new_zeros(1), torch.cumsum(counts, 0)]).to(i32).contiguous()
             self.ws_loop = ops.bo_fixed_loop_workspace(T, self.lattice, dev)
             self.fallback_trials = 0
         elif self.lattice is not None:
@@ -340,7 +344,7 @@ class BatchedBO:
         self._timed("bo_fixed_loop", self.n_max, lambda: ops.bo_fixed_loop(
             self.lattice, self.ktabY, self.ktab_id, self.order, self.obj, self.surf_id, self.X, self.y, self.n, self.theta,
             self.best_f, self.yall, self.picked, self.nit, self.status, self.max_iter, self.acq_id, self.acq_param,
-            self.var_floor, self.tol, self.optimal_y, ws=self.ws_loop))
+            self.var_floor, self.tol, self.optimal_y, ws=self.ws_loop, slot_start=self.slot_start))
         self.launches += 1
         self.iters_done = self.max_iter
 

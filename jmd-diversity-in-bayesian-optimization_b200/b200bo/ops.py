@@ -485,7 +485,7 @@ def bo_fixed_loop_workspace(T: int, lat, device) -> torch.Tensor:
 
 
 def bo_fixed_loop(lat, ktabY, ktab_id, order, obj, surf_id, X, y, n, theta, best_f, yall, picked, nit, status, max_iter,
-                  acq_id=EI, acq_param=0.0, var_floor=VAR_FLOOR, tol=0.1, optimal_y=100.0, ws=None):
+                  acq_id=EI, acq_param=0.0, var_floor=VAR_FLOOR, tol=0.1, optimal_y=100.0, ws=None, slot_start=None):
     """K-F: every iteration of every trial in ONE launch (BOloop_fixparam's loop, Src/BO.py:404-446). In place on
     X / y / n / best_f / yall / picked / nit / status; trials flagged ST_FALLBACK come back untouched."""
     lib = _lib.load()
@@ -500,7 +500,11 @@ def bo_fixed_loop(lat, ktabY, ktab_id, order, obj, surf_id, X, y, n, theta, best
     T, n_max = y.shape
     if ws is None:
         ws = bo_fixed_loop_workspace(T, lat, X.device)
-    check(lib.b200bo_bo_fixed_loop(lat.Gx, lat.Gy, lat.x0, lat.y0, lat.h, _ptr(ktabY), _ptr(ktab_id), _ptr(order), _ptr(obj),
+    H = ktabY.shape[0]
+    if slot_start is not None:
+        _cu(slot_start, torch.int32, "slot_start")
+    check(lib.b200bo_bo_fixed_loop(lat.Gx, lat.Gy, lat.x0, lat.y0, lat.h, _ptr(ktabY), _ptr(ktab_id), _ptr(order),
+                                   _ptr(slot_start), H, _ptr(obj),
                                    _ptr(surf_id), _ptr(X), _ptr(y), _ptr(n), _ptr(theta), _ptr(best_f), _ptr(yall),
                                    _ptr(picked), _ptr(nit), _ptr(status), T, n_max, int(max_iter), int(acq_id),
                                    float(acq_param), float(var_floor), float(tol), float(optimal_y), _ptr(ws), ws.numel(),

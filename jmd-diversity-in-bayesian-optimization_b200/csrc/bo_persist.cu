@@ -72,6 +72,10 @@ struct BoPersistParams {
   unsigned long long* stats; // (8) optional counters: [0] acquisitions, [1] exact evaluations, [2] batches
   int T, n_max, max_iter, acq_id, prune, Gs, rows_pad, P;
   double acq_param, var_floor, tol, optimal_y;
+  // two-trials-per-CTA kernel (bo_fixed_loop2_kernel)
+  const int32_t* slot_start; // (H + 1) first position in `order` of every table slot, or null (one slot, all trials)
+  int32_t* slot_cnt;         // (H) per-slot work-queue heads (zero before the launch)
+  int H;
 };
 
 __host__ __device__ inline size_t bp_align16(size_t v) { return (v + 15) & ~(size_t)15; }
@@ -478,6 +482,441 @@ bo_fixed_loop_kernel(const BoPersistParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Two trials per CTA. The one-trial kernel above spends about half of an iteration outside the look-up loop — the
+// row append (a serial dependency chain over a 110 x 110 triangle), the state pass through L2, the exact evaluations,
+// the arg-max and the bookkeeping — all latency-bound phases during which the shared-memory pipe idles. Here the CTA's
+// 1024 threads form two halves of 512 that run two DIFFERENT trials with the SAME hyper-parameters out of ONE table,
+// each half on its own named barrier, so the latency-bound phases of one trial overlap the look-up loop of the other.
+// To make room for the second trial's L^-1 the table is the unsigned one (Gy x Gx: |dy|, |dx|; 80 KB instead of
+// 159 KB): the row offset of candidate c of a thread becomes |e - c P rowbytes| + a0, ONE integer instruction
+// (__sad -> VABSDIFF) per look-up. A thread owns 2 x BP_C = 20 rows of one lattice column (rows ph + c P2), folded in
+// two passes of 10 so the accumulators stay in registers.
+// Work distribution: trials sorted by table slot; a CTA visits the slots round-robin from a staggered start, both
+// halves pull trials from the slot's queue until it is empty, then the CTA (a CTA-wide barrier) loads the next table.
+// The EI prune test reads a per-candidate fp32 key kept in registers from the state pass (no second trip to L2), and
+// every warp fetches the objective value of its own best candidate before the CTA-level arg-max (the winner's value is
+// then already on chip).
+constexpr int BP2_HALF = 512;
+constexpr int BP2_WARPS = BP2_HALF / 32;
+constexpr int BP2_C = 2 * BP_C;          // candidate rows per thread
+
+struct Bp2Smem {
+  size_t table, half0, W, obs, kv, lv, yv, mask, stack, red_val, red_idx, red_obj, ctl, thr, half_bytes, total;
+};
+
+__host__ __device__ inline int bp2_phases(int Gy) { return (Gy + BP2_C - 1) / BP2_C; }
+
+__host__ __device__ inline Bp2Smem bp2_layout(int Gx, int Gy, int n_max) {
+  Bp2Smem L;
+  // rows of the last row phase past Gy are read (and discarded): |row - cy| <= (P2 * BP2_C - 1)
+  const int rows = bp2_phases(Gy) * BP2_C;
+  size_t o = 0;
+  L.table = o; o = bp_align16(o + (size_t)rows * Gx * 8);
+  L.half0 = o;
+  size_t h = 0;
+  L.W = h;     h = bp_align16(h + (size_t)n_max * (n_max + 1) / 2 * 8);
+  L.obs = h;   h = bp_align16(h + (size_t)n_max * sizeof(BpObs));
+  L.kv = h;    h = bp_align16(h + (size_t)n_max * 8);
+  L.lv = h;    h = bp_align16(h + (size_t)n_max * 8);
+  L.yv = h;    h = bp_align16(h + (size_t)n_max * 8);
+  L.mask = h;  h = bp_align16(h + (size_t)((Gx * Gy + 31) / 32) * 4);
+  L.stack = h; h = bp_align16(h + (size_t)BP2_WARPS * BP_STACK * 4);
+  L.red_val = h; h = bp_align16(h + BP2_WARPS * 8);
+  L.red_idx = h; h = bp_align16(h + BP2_WARPS * 4);
+  L.red_obj = h; h = bp_align16(h + BP2_WARPS * 4);
+  L.ctl = h;   h = bp_align16(h + 16 * 4);
+  L.thr = h;   h = bp_align16(h + 16);
+  L.half_bytes = h;
+  L.total = o + 2 * h;
+  return L;
+}
+
+__device__ __forceinline__ void bp2_sync(int half) { asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(BP2_HALF) : "memory"); }
+
+template <int GXC, int PC>
+__global__ void __launch_bounds__(BP_THREADS, 1)
+bo_fixed_loop2_kernel(const BoPersistParams p) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const Bp2Smem L = bp2_layout(p.Gx, p.Gy, p.n_max);
+  const int half = threadIdx.x >> 9;
+  const int tid = threadIdx.x & (BP2_HALF - 1), lane = tid & 31, warp = tid >> 5;
+  unsigned char* hb = smraw + L.half0 + (size_t)half * L.half_bytes;
+  double* table = reinterpret_cast<double*>(smraw + L.table);
+  double* W = reinterpret_cast<double*>(hb + L.W);
+  BpObs* obs = reinterpret_cast<BpObs*>(hb + L.obs);       // here: rowoff = cy * rowbytes (>= 0)
+  double* kv = reinterpret_cast<double*>(hb + L.kv);
+  double* lv = reinterpret_cast<double*>(hb + L.lv);
+  double* yv = reinterpret_cast<double*>(hb + L.yv);
+  unsigned* omask = reinterpret_cast<unsigned*>(hb + L.mask);
+  int* stk = reinterpret_cast<int*>(hb + L.stack) + warp * BP_STACK;
+  double* red_val = reinterpret_cast<double*>(hb + L.red_val);
+  int* red_idx = reinterpret_cast<int*>(hb + L.red_idx);
+  float* red_obj = reinterpret_cast<float*>(hb + L.red_obj);
+  int* ctl = reinterpret_cast<int*>(hb + L.ctl);           // [0] queue position, [1] picked idx, [2] flags, [3] stop
+  unsigned long long* thr_bits = reinterpret_cast<unsigned long long*>(hb + L.thr);
+  const int Gx = GXC ? GXC : p.Gx;
+  const int P = PC ? PC : p.P;                             // row phases of the 20-row ownership
+  const int Gy = p.Gy, G = p.G;
+  const int rowbytes = Gx * 8;
+  const int cstride = P * rowbytes;
+  const int mask_words = (G + 31) >> 5;
+  double* mu_s = p.state + ((size_t)blockIdx.x * 2 + half) * 2 * p.Gs;
+  double* ss_s = mu_s + p.Gs;
+  // zero the padding rows once (rows >= Gy are only reached by the dead rows of the last row phase)
+  for (int e = Gy * Gx + (int)threadIdx.x; e < P * BP2_C * Gx; e += BP_THREADS) table[e] = 0.0;
+  int ph, gx;
+  bool active;
+  {
+    const int FG = Gx >> 5, LC = Gx & 31;
+    const int nfull = P * FG * 32;
+    if (tid < nfull) {
+      ph = warp / FG;
+      gx = (warp - ph * FG) * 32 + lane;
+      active = true;
+    } else {
+      const int q = tid - nfull;
+      active = LC > 0 && q < P * LC;
+      ph = active ? q / LC : 0;
+      gx = active ? FG * 32 + (q - ph * LC) : 0;
+    }
+  }
+  const int g0 = ph * Gx + gx;
+  const int gstep = P * Gx;
+  const int tab_rows = 2 * Gy - 1;
+  long long tk = 0;
+#define BP2_TICK(k) do { if (p.stats && threadIdx.x == 0) { const long long now__ = clock64(); atomicAdd(&p.stats[k], (unsigned long long)(now__ - tk)); tk = now__; } } while (0)
+
+  const int H = p.H > 0 ? p.H : 1;
+  const int slot_first = (int)(((long long)blockIdx.x * H) / gridDim.x);
+  for (int si = 0; si < H; ++si) {
+    int slot = slot_first + si;
+    if (slot >= H) slot -= H;
+    const int q_lo = p.slot_start ? p.slot_start[slot] : 0;
+    const int q_hi = p.slot_start ? p.slot_start[slot + 1] : p.T;
+    if (q_hi <= q_lo) continue;                                        // CTA-uniform
+    __syncthreads();                                                   // both halves are done with the previous table
+    {
+      // the dy >= 0 half of the y-signed table: rows Gy-1 .. 2Gy-2 of the slot
+      const double* src1 = p.ktabY + ((size_t)slot * tab_rows + (Gy - 1)) * Gx;
+      const int cnt = Gy * Gx;
+      if ((cnt & 1) || ((((size_t)slot * tab_rows + (Gy - 1)) * Gx) & 1)) {
+        for (int e = threadIdx.x; e < cnt; e += BP_THREADS) table[e] = __ldg(src1 + e);
+      } else {
+        const double2* src = reinterpret_cast<const double2*>(src1);
+        double2* dst = reinterpret_cast<double2*>(table);
+        for (int e = threadIdx.x; e < (cnt >> 1); e += BP_THREADS) dst[e] = __ldg(src + e);
+      }
+    }
+    __syncthreads();
+
+    for (;;) {                                                         // this half's trials of the slot
+      if (tid == 0) ctl[0] = atomicAdd(&p.slot_cnt[slot], 1);
+      bp2_sync(half);
+      const int q = q_lo + ctl[0];
+      if (q >= q_hi) break;                                            // half-uniform
+      const int t = p.order ? p.order[q] : q;
+      const int n0 = p.n[t];
+      const double noise = p.theta[(size_t)t * 4], cst = p.theta[(size_t)t * 4 + 1], sc = p.theta[(size_t)t * 4 + 2];
+      double* Xt = p.X + (size_t)t * p.n_max * 2;
+      double* yt = p.y + (size_t)t * p.n_max;
+      double* yall = p.yall + (size_t)t * (p.max_iter + 2);
+      int32_t* picked = p.picked + (size_t)t * (p.max_iter > 0 ? p.max_iter : 1);
+      const float* objt = p.obj + (size_t)p.surf_id[t] * G;
+      for (int w = tid; w < mask_words; w += BP2_HALF) omask[w] = 0u;
+      if (tid == 0) { ctl[2] = 0; ctl[3] = 0; }
+      bp2_sync(half);
+      for (int j = tid; j < n0 && j < p.n_max; j += BP2_HALF) {
+        const double x = Xt[2 * j], yy = Xt[2 * j + 1];
+        const double fx = rint((x - p.x0) / p.h), fy = rint((yy - p.y0) / p.h);
+        const bool on = (__dadd_rn(p.x0, __dmul_rn(p.h, fx)) == x) && (__dadd_rn(p.y0, __dmul_rn(p.h, fy)) == yy) &&
+                        fx >= 0.0 && fy >= 0.0 && fx < (double)Gx && fy < (double)Gy;
+        const int xi = on ? (int)fx : 0, yi = on ? (int)fy : 0;
+        obs[j].cx = xi;
+        obs[j].rowoff = yi * rowbytes;
+        yv[j] = yt[j] - cst;
+        if (!on) atomicOr(&ctl[2], B200BO_ST_OFF_LATTICE | B200BO_ST_FALLBACK);
+      }
+      if (warp == 0) {
+        double b = -INFINITY;
+        for (int j = lane; j < n0 && j < p.n_max; j += 32) b = fmax(b, yt[j]);
+        b = warp_max(b);
+        if (lane == 0) {
+          p.best_f[t] = b;
+          yall[0] = b;                                                 // result.yall.append(result.yopt), BO.py:146
+          p.nit[t] = 0;
+          red_val[0] = b;
+        }
+        for (int i = lane; i < p.max_iter; i += 32) picked[i] = -1;
+      }
+      bp2_sync(half);
+      double best = red_val[0];
+      int flags_cta = ctl[2];
+      bp2_sync(half);
+      if (n0 > p.n_max || n0 < 1) flags_cta |= B200BO_ST_FALLBACK;
+      const bool runnable = p.max_iter > 0 && !(flags_cta & B200BO_ST_FALLBACK);
+      int n_cur = n0;
+      int it_done = 0;
+
+      if (runnable) {
+        for (int m = 0; m < n_cur; ++m) {
+          if (p.stats && threadIdx.x == 0) tk = clock64();
+          // ---- append observation m
+          const int cxm = obs[m].cx, rom = obs[m].rowoff;
+          for (int j = tid; j < m; j += BP2_HALF) {
+            const int off = abs(rom - obs[j].rowoff) + abs(cxm - obs[j].cx) * 8;
+            kv[j] = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(table) + off);
+          }
+          bp2_sync(half);
+          for (int i = warp; i < m; i += BP2_WARPS) {                  // l = W k : one warp per row
+            const double* wr = W + (size_t)i * (i + 1) / 2;
+            double acc = 0.0;
+            for (int j = lane; j <= i; j += 32) acc = fma(wr[j], kv[j], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) lv[i] = acc;
+          }
+          bp2_sync(half);
+          double ll = 0.0;                                             // every warp computes the same bits
+          for (int j = lane; j < m; j += 32) ll = fma(lv[j], lv[j], ll);
+          ll = warp_sum(ll);
+          const double kappa = table[0] + noise;
+          const double lam2 = kappa - ll;
+          if (!(lam2 > 0.0)) {                                         // psd_safe_cholesky territory: hand the trial back
+            flags_cta |= B200BO_ST_FALLBACK;
+            break;
+          }
+          const double inv_lam = 1.0 / sqrt(lam2);
+          if (tid < m) {
+            double acc = 0.0, acc1 = 0.0;
+            int i = tid;
+            if ((m - i) & 1) { acc1 = W[(size_t)i * (i + 1) / 2 + tid] * lv[i]; ++i; }
+            for (; i < m; i += 2) {
+              acc = fma(W[(size_t)i * (i + 1) / 2 + tid], lv[i], acc);
+              acc1 = fma(W[(size_t)(i + 1) * (i + 2) / 2 + tid], lv[i + 1], acc1);
+            }
+            acc += acc1;
+            const double w = -acc * inv_lam;
+            W[(size_t)m * (m + 1) / 2 + tid] = w;
+            obs[tid].w = w;
+          }
+          if (tid == BP2_HALF - 1) {
+            W[(size_t)m * (m + 1) / 2 + m] = inv_lam;
+            obs[m].w = inv_lam;
+            const int gflat = (rom / rowbytes) * Gx + cxm;             // the appended observation is no longer selectable
+            omask[gflat >> 5] |= 1u << (gflat & 31);
+            thr_bits[0] = 0ull;
+          }
+          bp2_sync(half);
+          double zn = 0.0;                                             // z_m = W[m][:] . (y - c)
+          for (int j = lane; j <= m; j += 32) zn = fma(obs[j].w, yv[j], zn);
+          zn = warp_sum(zn);
+          const bool acquire = m >= n0 - 1;
+          const bool ei_prune = p.acq_id == B200BO_ACQ_EI && p.prune;
+          BP2_TICK(3);
+
+          // ---- fold row m into the state of the thread's 20 candidates, two passes of 10
+          unsigned surv = 0;                                           // bit c: candidate c still needs an exact value
+          float key[BP2_C];                                            // EI prune keys (registers)
+          float seed_u = -INFINITY;
+          int seed_c = -1;
+          double seed_mu = 0.0, seed_ss = 0.0;
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass) {
+            double v[BP_C];
+#pragma unroll
+            for (int c = 0; c < BP_C; ++c) v[c] = 0.0;
+            if (active) {
+              const unsigned tb32 = smem_u32(table);                   // shared-window address of the table
+              const int erow = (ph + pass * BP_C * P) * rowbytes;      // byte offset of the pass's first row
+#pragma unroll 2
+              for (int j = 0; j <= m; ++j) {
+                const int4 o = *reinterpret_cast<const int4*>(&obs[j]);   // {w.lo, w.hi, cy * rowbytes, cx}
+                const double ow = __hiloint2double(o.y, o.x);
+                const unsigned a0 = tb32 + (unsigned)(abs(gx - o.w) * 8);
+                const int e = o.z - erow;                              // (cy - first row) * rowbytes
+#pragma unroll
+                for (int c = 0; c < BP_C; ++c) {
+                  double kval;                                         // table[|row_c - cy|][|gx - cx|]: VABSDIFF + LDS.64
+                  asm("ld.shared.f64 %0, [%1];" : "=d"(kval) : "r"(__sad(e, c * cstride, a0)));
+                  v[c] = fma(ow, kval, v[c]);
+                }
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < BP_C; ++c) {
+              const int cc = pass * BP_C + c;
+              const bool live = active && (ph + cc * P) < Gy;
+              const int g = g0 + cc * gstep;
+              double mu = 0.0, ss = 0.0;
+              if (live && m > 0) { mu = mu_s[g]; ss = ss_s[g]; }
+              mu = fma(v[c], zn, mu);
+              ss = fma(v[c], v[c], ss);
+              if (live) { mu_s[g] = mu; ss_s[g] = ss; }
+              key[cc] = -INFINITY;
+              if (acquire && live) {
+                const bool masked = (omask[g >> 5] >> (g & 31)) & 1u;
+                if (!masked) {
+                  surv |= 1u << cc;
+                  if (ei_prune) {
+                    // skip x when sigma phi(u) / (1 + u^2) < thr (u < 0): u^2 / 2 - log(sigma) + log(1 + u^2) >
+                    // log(phi(0) / thr); the left side in fp32 with relative + absolute margins (a lower bound)
+                    const float df = (float)((cst + mu) - best);
+                    const float vf = fmaxf((float)(sc - ss), (float)p.var_floor);
+                    const float rv = __frcp_rn(vf);
+                    const float u = df * sqrtf(rv);
+                    if (u > seed_u) { seed_u = u; seed_c = cc; seed_mu = mu; seed_ss = ss; }
+                    if (df < 0.0f) {
+                      const float u2 = df * df * rv;
+                      float corr = 0.5f * __logf(vf);
+                      if (u2 < 1e30f) corr -= __logf(1.0f + u2);
+                      corr += 1e-3f + 1e-5f * fabsf(corr);
+                      key[cc] = 0.5f * u2 * (1.0f - 1e-5f) - corr;
+                    }
+                  }
+                }
+              }
+            }
+          }
+          BP2_TICK(4);
+          if (!acquire) { bp2_sync(half); continue; }
+
+          double best_v = -INFINITY;
+          int best_i = INT_MAX;
+          int flags = 0;
+          unsigned long long n_eval = 0, n_batch = 0;
+          if (ei_prune) {
+            if (seed_c >= 0) {                                         // an ATTAINED threshold for the whole trial
+              const double aq = acquisition<B200BO_ACQ_EI>(cst + seed_mu, sc - seed_ss, best, p.acq_param, p.var_floor);
+              const int g = g0 + seed_c * gstep;
+              if (isnan(aq) || aq == INFINITY) flags |= B200BO_ST_NONFINITE;
+              if (!isnan(aq)) { best_v = aq; best_i = g; }
+              surv &= ~(1u << seed_c);
+            }
+            if (p.stats) { n_eval += __popc(__ballot_sync(0xffffffffu, seed_c >= 0)); n_batch += 1; }
+            const double wb = warp_max(best_v);
+            if (lane == 0 && wb > 0.0 && wb < INFINITY) atomicMax(thr_bits, (unsigned long long)__double_as_longlong(wb));
+            bp2_sync(half);
+            BP2_TICK(6);
+            const double thr = __longlong_as_double((long long)thr_bits[0]);
+            if (thr > 0.0 && surv) {
+              // log(phi(0) / thr), rounded up into fp32
+              const double lbase = log(kInvSqrt2Pi / thr) * (1.0 + 1e-12) + 1e-12;
+              const float lb = __double2float_ru(lbase);
+#pragma unroll
+              for (int cc = 0; cc < BP2_C; ++cc)
+                if (key[cc] > lb) surv &= ~(1u << cc);
+            }
+          }
+          BP2_TICK(7);
+          {
+            int cnt = 0;
+            auto eval_batch = [&](int first, int count) {
+              if (lane < count) {
+                const int g = stk[first + lane];
+                const double aq = bp_acq(p.acq_id, cst + mu_s[g], sc - ss_s[g], best, p.acq_param, p.var_floor);
+                if (isnan(aq) || aq == INFINITY) flags |= B200BO_ST_NONFINITE;
+                if (!isnan(aq) && better(aq, g, best_v, best_i)) { best_v = aq; best_i = g; }
+              }
+              n_eval += count; n_batch += 1;
+            };
+            const unsigned any = __reduce_or_sync(0xffffffffu, surv);
+#pragma unroll 1
+            for (int cc = 0; cc < BP2_C; ++cc) {
+              if (!((any >> cc) & 1u)) continue;                       // warp-uniform
+              const bool push = (surv >> cc) & 1u;
+              const unsigned bal = __ballot_sync(0xffffffffu, push);
+              if (push) stk[cnt + __popc(bal & ((1u << lane) - 1u))] = g0 + cc * gstep;
+              cnt += __popc(bal);
+              __syncwarp();
+              if (cnt >= 32) {
+                eval_batch(cnt - 32, 32);
+                cnt -= 32;
+                __syncwarp();
+              }
+            }
+            if (cnt > 0) eval_batch(0, cnt);
+          }
+          warp_argmax(best_v, best_i);
+          flags = __reduce_or_sync(0xffffffffu, flags);
+          if (lane == 0) {
+            red_val[warp] = best_v;
+            red_idx[warp] = best_i;
+            red_obj[warp] = best_i != INT_MAX ? __ldg(&objt[best_i]) : 0.0f;   // fetched while the other warps finish
+            if (flags) atomicOr(&ctl[2], flags);
+            if (p.stats) {
+              atomicAdd(&p.stats[1], n_eval);
+              atomicAdd(&p.stats[2], n_batch);
+              if (warp == 0) atomicAdd(&p.stats[0], 1ull);
+            }
+          }
+          bp2_sync(half);
+          BP2_TICK(8);
+          // ---- bookkeeping (BO.py:104,164-169,152,241): warp 0 finishes the arg-max, its lane 0 appends
+          if (warp == 0) {
+            const int my_idx = lane < BP2_WARPS ? red_idx[lane] : INT_MAX;
+            double bv = lane < BP2_WARPS ? red_val[lane] : -INFINITY;
+            int bi = my_idx;
+            warp_argmax(bv, bi);
+            const unsigned who = __ballot_sync(0xffffffffu, my_idx == bi && lane < BP2_WARPS);
+            if (lane == 0) {
+              const int it = m - (n0 - 1);
+              int stop = 0;
+              if (bi == INT_MAX) {                                     // nothing selectable
+                atomicOr(&ctl[2], B200BO_ST_ALL_MASKED);
+                bi = -1;
+                stop = 1;
+              } else if (m + 1 >= p.n_max) {
+                bi = -1;
+                stop = 1;
+              } else {
+                const int gy = bi / Gx, gxx = bi - gy * Gx;
+                const double xn = __dadd_rn(p.x0, __dmul_rn(p.h, (double)gxx)), yn = __dadd_rn(p.y0, __dmul_rn(p.h, (double)gy));
+                const double val = (double)red_obj[__ffs(who) - 1];    // torch.tensor(obj_func(new_x), dtype=float32)
+                Xt[2 * (m + 1)] = xn;
+                Xt[2 * (m + 1) + 1] = yn;
+                yt[m + 1] = val;
+                obs[m + 1].cx = gxx;
+                obs[m + 1].rowoff = gy * rowbytes;
+                yv[m + 1] = val - cst;
+                const double b = fmax(best, val);
+                picked[it] = bi;
+                yall[it + 1] = b;
+                p.nit[t] = it + 1;
+                red_val[0] = b;
+                stop = (!((p.optimal_y - b) > p.tol) || (it + 1 >= p.max_iter)) ? 2 : 0;
+              }
+              ctl[1] = bi;
+              ctl[3] = stop;
+            }
+          }
+          bp2_sync(half);
+          const int stop = ctl[3];
+          if (ctl[1] >= 0) {
+            best = red_val[0];
+            n_cur = m + 2;
+            it_done = m - (n0 - 1) + 1;
+          }
+          bp2_sync(half);
+          BP2_TICK(9);
+          if (stop) break;
+        }
+      }
+      if (tid == 0) {
+        flags_cta |= ctl[2];
+        const bool ok = runnable && !(flags_cta & B200BO_ST_FALLBACK);
+        const int k = ok ? it_done : 0;
+        const double last = yall[k];
+        for (int i = k + 1; i < p.max_iter + 2; ++i) yall[i] = last;
+        if (ok) p.best_f[t] = best;
+        p.n[t] = ok ? (n0 + it_done) : n0;
+        if (!ok) p.nit[t] = 0;
+        if (flags_cta) atomicOr(&p.status[t], flags_cta);
+      }
+      bp2_sync(half);
+    }
+  }
+}
+
 // y-signed table: ktabY[slot][(dy + Gy-1) Gx + dx] = s k(h sqrt(dx^2 + dy^2) / l), dx >= 0; same device function and
 // operands as kernel_table_kernel / the generic path (bit-identical values)
 __global__ void __launch_bounds__(256)
@@ -518,10 +957,17 @@ int b200bo_kernel_table_ysigned(const double* theta, int H, int kernel_id, doubl
   return 0;
 }
 
+static int bp2_fits(int Gx, int Gy, int n_max) {
+  using namespace b200bo;
+  if ((long long)bp2_phases(Gy) * Gx > BP2_HALF) return 0;        // one thread of a half per (row phase, column)
+  return bp2_layout(Gx, Gy, n_max).total <= 232448 ? 1 : 0;
+}
+
 int b200bo_bo_fixed_loop_supported(int Gx, int Gy, int n_max) {
   using namespace b200bo;
   if (Gx < 1 || Gy < 1 || n_max < 1 || n_max > B200BO_NMAX) return 0;
   if ((long long)Gx * Gy > (1 << 24)) return 0;
+  if (bp2_fits(Gx, Gy, n_max)) return 1;
   if ((long long)bp_phases(Gy) * Gx > BP_THREADS) return 0;        // one thread per (row phase, column)
   return bp_layout(Gx, Gy, n_max).total <= 232448 ? 1 : 0;       // 227 KB of dynamic shared memory per CTA on sm_100
 }
@@ -534,14 +980,15 @@ int b200bo_bo_fixed_loop_ctas(int T) {
 size_t b200bo_bo_fixed_loop_workspace_bytes(int T, int Gx, int Gy) {
   if (T <= 0 || Gx <= 0 || Gy <= 0) return 0;
   const size_t Gs = ((size_t)Gx * Gy + 15) & ~(size_t)15;
-  return 256 + (size_t)b200bo_bo_fixed_loop_ctas(T) * 2 * Gs * sizeof(double);
+  // header | per-CTA state (two trials per CTA in the two-halves kernel) | per-slot queue heads (<= T slots)
+  return 256 + (size_t)b200bo_bo_fixed_loop_ctas(T) * 4 * Gs * sizeof(double) + (size_t)T * sizeof(int32_t);
 }
 
 int b200bo_bo_fixed_loop(int Gx, int Gy, double x0, double y0, double h, const double* ktabY, const int32_t* ktab_id,
-                         const int32_t* order, const float* obj, const int32_t* surf_id, double* X, double* y, int32_t* n,
-                         const double* theta, double* best_f, double* yall, int32_t* picked, int32_t* nit,
-                         int32_t* status, int T, int n_max, int max_iter, int acq_id, double acq_param, double var_floor,
-                         double tol, double optimal_y, void* ws, size_t ws_bytes, void* stream) {
+                         const int32_t* order, const int32_t* slot_start, int H, const float* obj, const int32_t* surf_id,
+                         double* X, double* y, int32_t* n, const double* theta, double* best_f, double* yall, int32_t* picked,
+                         int32_t* nit, int32_t* status, int T, int n_max, int max_iter, int acq_id, double acq_param,
+                         double var_floor, double tol, double optimal_y, void* ws, size_t ws_bytes, void* stream) {
   using namespace b200bo;
   const char* who = "bo_fixed_loop";
   if (T < 0 || max_iter < 0 || !(h > 0.0)) return arg_error("%s: bad sizes", who);
@@ -552,6 +999,8 @@ int b200bo_bo_fixed_loop(int Gx, int Gy, double x0, double y0, double h, const d
     return arg_error("%s: null pointer", who);
   if (acq_id < 0 || acq_id > 2) return arg_error("%s: acq_id=%d", who, acq_id);
   if (acq_id == B200BO_ACQ_UCB && !(acq_param >= 0.0)) return arg_error("%s: UCB beta < 0", who);
+  if (H < 1 || H > T) return arg_error("%s: H=%d table slots for T=%d trials", who, H, T);
+  if (H > 1 && (!ktab_id || !order || !slot_start)) return arg_error("%s: H > 1 needs ktab_id, order and slot_start", who);
   if (ws_bytes < b200bo_bo_fixed_loop_workspace_bytes(T, Gx, Gy)) return arg_error("%s: workspace too small", who);
   cudaStream_t st = as_stream(stream);
   BoPersistParams p;
@@ -569,12 +1018,41 @@ int b200bo_bo_fixed_loop(int Gx, int Gy, double x0, double y0, double h, const d
   static const int prune_env = [] { const char* e = getenv("B200BO_KB_PRUNE"); return e ? atoi(e) : 1; }();
   p.prune = prune_env;
   p.Gs = (int)((((size_t)Gx * Gy) + 15) & ~(size_t)15);
+  const int ctas1 = b200bo_bo_fixed_loop_ctas(T);
+  const size_t state_bytes = (size_t)ctas1 * 4 * p.Gs * sizeof(double);
+  p.slot_start = H > 1 ? slot_start : nullptr;
+  p.slot_cnt = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(ws) + 256 + state_bytes);
+  p.H = H;
+  cudaError_t e = cudaMemsetAsync(ws, 0, 256, st);
+  if (e != cudaSuccess) return cuda_status(e, who);
+  static const int dual_env = [] { const char* e = getenv("B200BO_KF_DUAL"); return e ? atoi(e) : 1; }();
+  if (dual_env && bp2_fits(Gx, Gy, n_max)) {
+    // two trials per CTA, unsigned table (see bo_fixed_loop2_kernel)
+    e = cudaMemsetAsync(p.slot_cnt, 0, (size_t)H * sizeof(int32_t), st);
+    if (e != cudaSuccess) return cuda_status(e, who);
+    p.P = bp2_phases(Gy);
+    p.rows_pad = p.P * BP2_C;
+    const size_t smem = bp2_layout(Gx, Gy, n_max).total;
+    const int sms = bp_sm_count();
+    const int ctas = (T + 1) / 2 < sms ? (T + 1) / 2 : sms;
+    if (Gx == 100 && p.P == 5) {
+      e = cudaFuncSetAttribute(bo_fixed_loop2_kernel<100, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_status(e, who);
+      bo_fixed_loop2_kernel<100, 5><<<ctas, BP_THREADS, smem, st>>>(p);
+    } else {
+      e = cudaFuncSetAttribute(bo_fixed_loop2_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_status(e, who);
+      bo_fixed_loop2_kernel<0, 0><<<ctas, BP_THREADS, smem, st>>>(p);
+    }
+    B200BO_CHECK_LAUNCH(who);
+    return 0;
+  }
+  if ((long long)bp_phases(Gy) * Gx > BP_THREADS || bp_layout(Gx, Gy, n_max).total > 232448)
+    return arg_error("%s: lattice %d x %d with n_max %d fits neither kernel variant", who, Gx, Gy, n_max);
   p.P = bp_phases(Gy);
   p.rows_pad = Gy - 1 + p.P * BP_C;
   const size_t smem = bp_layout(Gx, Gy, n_max).total;
-  cudaError_t e = cudaMemsetAsync(ws, 0, 256, st);
-  if (e != cudaSuccess) return cuda_status(e, who);
-  const int ctas = b200bo_bo_fixed_loop_ctas(T);
+  const int ctas = ctas1;
   if (Gx == 100 && p.P == 10) {
     e = cudaFuncSetAttribute(bo_fixed_loop_kernel<100, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e, who);
