@@ -467,6 +467,11 @@ def bench_other_configs(dev, surf, S):
         go = (lambda: [bos[0].run()]) if groups == 1 else (lambda: engine.run_concurrent(bos, streams))
         go()                                                       # warm-up
         torch.cuda.synchronize(dev)
+        account = theta is None and groups == 1                    # K-C roofline: per-launch events + evaluation counts
+        if account:
+            bos[0].profile = []
+            bos[0].fitter.account = True
+            bos[0].fitter.flops.zero_(); bos[0].fitter.evals.zero_()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
@@ -482,6 +487,18 @@ def bench_other_configs(dev, surf, S):
                      "concurrent_groups": groups}
         if theta is None:
             out[name]["fit_evaluations_mean_last"] = float(torch.cat([b.fitter.iters[:, 1] for b in bos]).float().mean().item())
+        if account:
+            fit_ms = sum(a.elapsed_time(b) for nm, _, a, b in bos[0].profile if nm == "fit")
+            flops, evals = float(bos[0].fitter.flops.item()), float(bos[0].fitter.evals.item())
+            peak = 37.055
+            out[name]["roofline_kc"] = {"bound": "tensor", "bound_detail": "FP64 pipe (DFMA; profiles/fp64_peaks_r1.json)",
+                                        "kernel": "gp_fit_sweep_kernel<NB,OW> (K-C, fused L-BFGS fit)",
+                                        "achieved": flops / (fit_ms * 1e-3) / 1e12 if fit_ms else None, "peak": peak,
+                                        "unit": "TFLOP/s", "frac": flops / (fit_ms * 1e-3) / 1e12 / peak if fit_ms else None,
+                                        "flops_model": "n^3 + 6 n^2 per marginal-likelihood evaluation (SURVEY.md 8d) x evaluations run",
+                                        "evaluations": evals, "fit_ms_total": fit_ms, "fit_share_of_run": fit_ms * 1e-3 / (sec * reps)}
+            bos[0].profile = None
+            bos[0].fitter.account = False
 
     theta = torch.tensor(THETA, dtype=torch.float64, device=dev)
     run("configs[2]_fit_every_iteration_tol_disabled", ops.Lattice(100, 100), 1000, 100, None, -1.0)

@@ -38,6 +38,10 @@ class LBFGSFitter:
         self.last_launches = 0
         self.last_rounds = 0
         self.fused = bool(fused)
+        # optional accounting (bench.py): algorithmic flops of the evaluations run so far, n^3 + 6 n^2 each
+        self.account = False
+        self.flops = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.evals = torch.zeros(1, dtype=torch.float64, device=dev)
 
     def fit_into(self, X, y, n, kernel_id, theta_out, status=None, n_hint=0):
         """Fit every trial with n[t] > 0 from the default start; writes ACTUAL theta (T,4) into theta_out."""
@@ -56,6 +60,11 @@ class LBFGSFitter:
                                     self.max_ls, self.max_rounds, s), "gp_fit")
             self.last_launches = 1
             self.last_rounds = 0
+            if self.account:
+                nf = n.clamp(min=0).double()
+                ev = torch.where(n > 0, self.iters[:, 1], torch.zeros_like(self.iters[:, 1])).double()
+                self.flops += (ev * (nf ** 3 + 6.0 * nf ** 2)).sum()
+                self.evals += ev.sum()
             return theta_out
         check(lib.b200bo_lbfgs_init(p(self.state), p(self.xt), p(self.raw0), self.raw0_per_trial, p(self.n_eval), p(n), T,
                                     NOISE_LB, s), "lbfgs_init")

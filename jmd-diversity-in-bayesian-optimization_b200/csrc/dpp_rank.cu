@@ -11,7 +11,7 @@
 //                                        launch (data_gen.py:758-842 re-scores them 256 times)
 //
 // The sort is a hand-written stable LSD radix sort of the 64-bit order-preserving image of the f64 scores with the set
-// index as payload: 8 passes of 8 bits, per pass a per-tile digit histogram, one exclusive scan over (digit, tile) and a
+// index as payload: 8 passes of 8 bits, per pass a per-tile digit histogram, a per-digit exclusive scan over the tiles and a
 // stable scatter (per-warp digit counters + __match_any_sync ranks: a warp owns a contiguous run of the tile, rounds of
 // 32 consecutive elements, so equal keys keep their order). HBM-bound: 2 x 8 passes x 12 B per set plus the gather.
 #include "common.cuh"
@@ -55,46 +55,50 @@ rs_hist_kernel(const unsigned long long* __restrict__ keys, long long N, int shi
   hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];          // digit-major: the scan order
 }
 
-// exclusive scan of `count` unsigned values in place, one CTA (count = 256 x tiles: 1.25 M at N = 10^7)
-__global__ void __launch_bounds__(1024) rs_scan_kernel(unsigned* __restrict__ a, int count) {
+// per digit (one CTA per digit row of the digit-major histogram): exclusive scan over the tiles in place, row total to
+// tot[digit]. Coalesced; the scatter kernel adds the digits-below offset (a 256-wide scan of tot) itself.
+__global__ void __launch_bounds__(1024) rs_rowscan_kernel(unsigned* __restrict__ hist, int nblocks, unsigned* __restrict__ tot) {
   __shared__ unsigned wsum[32];
-  __shared__ unsigned carry;
+  __shared__ unsigned carry_s;
+  unsigned* row = hist + (size_t)blockIdx.x * nblocks;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int per = (count + 1023) / 1024;
-  const int lo = min(count, tid * per), hi = min(count, lo + per);
-  unsigned s = 0;
-  for (int i = lo; i < hi; ++i) s += a[i];
-  unsigned incl = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) wsum[warp] = incl;
-  if (tid == 0) carry = 0;
+  if (tid == 0) carry_s = 0u;
   __syncthreads();
-  if (warp == 0) {
-    unsigned w = wsum[lane], wi = w;
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int i = base + tid;
+    const unsigned v = i < nblocks ? row[i] : 0u;
+    unsigned incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const unsigned t = __shfl_up_sync(0xffffffffu, wi, o);
-      if (lane >= o) wi += t;
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
-    wsum[lane] = wi - w;
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const unsigned w = wsum[lane];
+      unsigned wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    const unsigned carry = carry_s;
+    if (i < nblocks) row[i] = carry + wsum[warp] + incl - v;
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + wsum[31] + incl;
+    __syncthreads();
   }
-  __syncthreads();
-  unsigned run = wsum[warp] + incl - s;
-  for (int i = lo; i < hi; ++i) {
-    const unsigned t = a[i];
-    a[i] = run;
-    run += t;
-  }
+  if (tid == 0) tot[blockIdx.x] = carry_s;
 }
 
 __global__ void __launch_bounds__(RS_THREADS)
 rs_scatter_kernel(const unsigned long long* __restrict__ keys_in, const int32_t* __restrict__ vals_in, long long N, int shift,
-                  int nblocks, const unsigned* __restrict__ bases, unsigned long long* __restrict__ keys_out,
-                  int32_t* __restrict__ vals_out) {
+                  int nblocks, const unsigned* __restrict__ bases, const unsigned* __restrict__ tot,
+                  unsigned long long* __restrict__ keys_out, int32_t* __restrict__ vals_out) {
   __shared__ unsigned cnt[RS_WARPS][RS_BINS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&cnt[0][0])[i] = 0u;
@@ -120,8 +124,21 @@ rs_scatter_kernel(const unsigned long long* __restrict__ keys_in, const int32_t*
   }
   __syncthreads();
   {
-    // per digit: global base of this tile, then the warps of the tile in order
-    unsigned run = bases[(size_t)tid * nblocks + blockIdx.x];
+    // per digit: keys with a smaller digit (256-wide exclusive scan of the digit totals), then this digit's keys in the
+    // tiles before this one, then the warps of the tile in order
+    __shared__ unsigned dsum[RS_WARPS];
+    const unsigned tv = tot[tid];
+    unsigned incl = tv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) dsum[warp] = incl;
+    __syncthreads();
+    unsigned below = incl - tv;
+    for (int w = 0; w < warp; ++w) below += dsum[w];
+    unsigned run = below + bases[(size_t)tid * nblocks + blockIdx.x];
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) {
       const unsigned t = cnt[w][tid];
@@ -298,7 +315,7 @@ size_t b200bo_dpp_rank_workspace_bytes(long long N) {
   if (N <= 0) return 0;
   const size_t n = (size_t)N;
   const size_t keys = ((n * 8 + 255) / 256) * 256, vals = ((n * 4 + 255) / 256) * 256;
-  return 2 * keys + 2 * vals + (size_t)rs_tiles(N) * RS_BINS * sizeof(unsigned) + 256;
+  return 2 * keys + 2 * vals + ((size_t)rs_tiles(N) + 1) * RS_BINS * sizeof(unsigned) + 256;
 }
 
 int b200bo_dpp_rank(const double* z, long long N, const int32_t* pos, int k, const double* pool, int pool_size,
@@ -319,14 +336,15 @@ int b200bo_dpp_rank(const double* z, long long N, const int32_t* pos, int k, con
   int32_t* vals[2] = {reinterpret_cast<int32_t*>(w + 2 * keys_b), reinterpret_cast<int32_t*>(w + 2 * keys_b + vals_b)};
   unsigned* hist = reinterpret_cast<unsigned*>(w + 2 * keys_b + 2 * vals_b);
   const int tiles = rs_tiles(N);
+  unsigned* tot = hist + (size_t)tiles * RS_BINS;
   const int blocks = (int)((N + 255) / 256 < 1184 ? (N + 255) / 256 : 1184);
   rs_keys_kernel<<<blocks, 256, 0, st>>>(z, N, keys[0], vals[0]);
   int cur = 0;
   for (int pass = 0; pass < 8; ++pass) {
     const int shift = pass * 8;
     rs_hist_kernel<<<tiles, RS_THREADS, 0, st>>>(keys[cur], N, shift, tiles, hist);
-    rs_scan_kernel<<<1, 1024, 0, st>>>(hist, tiles * RS_BINS);
-    rs_scatter_kernel<<<tiles, RS_THREADS, 0, st>>>(keys[cur], vals[cur], N, shift, tiles, hist, keys[cur ^ 1], vals[cur ^ 1]);
+    rs_rowscan_kernel<<<RS_BINS, 1024, 0, st>>>(hist, tiles, tot);
+    rs_scatter_kernel<<<tiles, RS_THREADS, 0, st>>>(keys[cur], vals[cur], N, shift, tiles, hist, tot, keys[cur ^ 1], vals[cur ^ 1]);
     cur ^= 1;
   }
   const int kk = (pos_sorted || dist) ? k : 1;

@@ -1,4 +1,4 @@
-"""Small single-kernel workloads for ncu captures: python tools/ncu_targets.py {dpp|inc|large|boot|wildcat}"""
+"""Small single-kernel workloads for ncu captures: python tools/ncu_targets.py {dpp|inc|large|boot|wildcat|kf|rank}"""
 import os, sys
 import numpy as np
 import torch
@@ -45,5 +45,22 @@ elif what == "inc":
     bo = engine.BatchedBO(pts, obj, sid, pts[idx], obj[sid.long()[:, None], idx].double(), 60, theta=theta, tol=-1.0, lattice=lat,
                           check_every=0, posterior="incremental")
     bo.run()
+elif what == "kf":
+    # the persistent fixed-theta loop on the bench shape: T trials (env T, default 12 500) x 100 iterations, ONE launch
+    gen = objectives.objectives()
+    S, T = 256, int(os.environ.get("T", 12500))
+    fam = [(s, r) for s in (0.2, 0.4, 0.6, 0.8) for r in (0.2, 0.4, 0.6, 0.8)]
+    surf = gen.wildcatwells_batch([s // 16 for s in range(S)], [fam[s % 16][0] for s in range(S)], [fam[s % 16][1] for s in range(S)], device=dev)
+    obj = surf[:, :100, :100].reshape(S, -1).contiguous()
+    idx = torch.as_tensor(np.stack([rng.choice(10000, 10, replace=False) for _ in range(T)]), device=dev)
+    sid = (torch.arange(T, device=dev) % S).int()
+    theta = torch.tensor([0.0017619397258386016, 41.82688735961914, 190.43237411499024, 9.869467], dtype=torch.float64, device=dev)
+    bo = engine.BatchedBO(pts, obj, sid, pts[idx], obj[sid.long()[:, None], idx].double(), 100, theta=theta, tol=-1.0, lattice=lat,
+                          check_every=0, posterior="persistent")
+    bo.run()
+elif what == "rank":
+    z = torch.as_tensor(rng.normal(size=10_000_000), device=dev)
+    for _ in range(2):
+        ops.dpp_rank(z)
 torch.cuda.synchronize()
 print("done", what)
