@@ -443,7 +443,7 @@ def bench_other_configs(dev, surf, S):
     out = {}
     rng = np.random.default_rng(99)
 
-    def run(name, lat, T, iters, theta, tol, reps=1, groups=1):
+    def run(name, lat, T, iters, theta, tol, reps=1, groups=1, posterior="full"):
         G = lat.G
         pts = lat.points(dev)
         if lat.h == 1.0:
@@ -462,7 +462,7 @@ def bench_other_configs(dev, surf, S):
         for lo, hi in zip(cuts[:-1], cuts[1:]):
             fitter = None if theta is not None else fit.LBFGSFitter(hi - lo, dev)
             bos.append(engine.BatchedBO(pts, obj, sid[lo:hi], X0[lo:hi], y0[lo:hi], iters, theta=theta, tol=tol,
-                                        fitter=fitter, lattice=lat))
+                                        fitter=fitter, lattice=lat, posterior=posterior))
         streams = [torch.cuda.Stream(dev) for _ in bos]
         go = (lambda: [bos[0].run()]) if groups == 1 else (lambda: engine.run_concurrent(bos, streams))
         go()                                                       # warm-up
@@ -506,6 +506,8 @@ def bench_other_configs(dev, surf, S):
     run("configs[2]_fit_every_iteration_tol_disabled_3_streams", ops.Lattice(100, 100), 1000, 100, None, -1.0, groups=3)
     run("configs[2]_fit_every_iteration_tol_0.1_3_streams", ops.Lattice(100, 100), 1000, 100, None, 0.1, groups=3)
     run("configs[3]_grid200_fixed_theta_slice", ops.Lattice(200, 200, 0.0, 0.0, 0.5), 1184, 100, theta, -1.0)
+    run("configs[3]_grid200_fixed_theta_slice_incremental", ops.Lattice(200, 200, 0.0, 0.0, 0.5), 1184, 100, theta, -1.0,
+        posterior="incremental")
     # configs[0]: ONE BO run through the reference-facing API (optimizer.optimize -> BOloop_fixparam), 10 initial
     # points, fixed theta, EI over the 100 x 100 lattice, 50 iterations — latency of a single trial, wall clock
     import objectives as objmod

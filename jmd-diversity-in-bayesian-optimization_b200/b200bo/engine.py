@@ -107,9 +107,16 @@ class BatchedBO:
         if posterior == "persistent" and not can_persist:
             raise ops._lib.B200boError("posterior='persistent' needs fixed theta, append=True, no theta_rest and a candidate "
                                        "lattice whose kernel table fits shared memory (100x100 with n0+max_iter <= 116)")
+        # incremental: the same O(n) update per candidate with the (mu, var) state in HBM and the table in L1 / L2 — for
+        # fixed theta on lattices whose table does not fit shared memory (the 200 x 200 lattice of BASELINE configs[3]:
+        # 4 x the full recomputation's throughput); "auto" takes it when the state (16 B per trial and candidate) fits
+        can_inc = (self.fixed and self.lattice is not None and self.append and theta_rest is None and self.max_iter > 0
+                   and 16 * T * self.G <= 48 << 30)
+        self.auto_fallback = posterior == "auto"               # auto-selected O(n) paths re-run failed trials through "full"
         if posterior == "auto":
-            posterior = "persistent" if can_persist else "full"
+            posterior = "persistent" if can_persist else ("incremental" if can_inc else "full")
         self.persistent = posterior == "persistent"
+        self.fallback_trials = 0
         self._kwargs = dict(kernel_id=kernel_id, acq_id=acq_id, acq_param=acq_param, tol=tol, optimal_y=optimal_y,
                             var_floor=var_floor, check_every=check_every, append=append)
         classic = not self.persistent                    # the per-iteration kernels' state (0.7 GB at T = 12 500)
@@ -139,7 +146,6 @@ class BatchedBO:
                 counts = torch.bincount(self.ktab_id.long(), minlength=uniq.shape[0])
                 self.slot_start = torch.cat([counts.new_zeros(1), torch.cumsum(counts, 0)]).to(i32).contiguous()
             self.ws_loop = ops.bo_fixed_loop_workspace(T, self.lattice, dev)
-            self.fallback_trials = 0
         elif self.lattice is not None:
             if self.fixed:
                 uniq, inv = torch.unique(self.theta, dim=0, return_inverse=True)
@@ -336,6 +342,10 @@ class BatchedBO:
             self._timed("fit", self.n0 + self.iters_done, lambda: self._fit(self.iters_done, self.n0 + self.iters_done))
         ops.bo_finalize(self.yall, self.nit, self.n, self.max_iter)
         self.launches += 1
+        if self.incremental and self.auto_fallback:
+            # a rank-1 append that met a non-positive pivot has no jitter rule (ST_CHOL_FAIL): such trials (none in
+            # practice) are re-run through the per-iteration factorisation, as the persistent path does
+            self._rerun_full((self.status & ops.ST_CHOL_FAIL) != 0)
         return BOResult(self.yall, self.picked[:, :self.max_iter], self.nit, self.status, self.X, self.y, self.n,
                         self.thetas)
 
@@ -352,7 +362,10 @@ class BatchedBO:
         """Trials the kernel handed back (ST_FALLBACK: an appended pivot was not positive, i.e. psd_safe_cholesky would
         have added jitter) are re-run through the per-iteration kernels, which implement the jitter rule; that needs one
         host look at the status words (the only synchronisation of the persistent path)."""
-        fb = (self.status & ops.ST_FALLBACK) != 0
+        self._rerun_full((self.status & ops.ST_FALLBACK) != 0)
+        return BOResult(self.yall, self.picked[:, :self.max_iter], self.nit, self.status, self.X, self.y, self.n, None)
+
+    def _rerun_full(self, fb):
         if bool(fb.any()):
             idx = torch.nonzero(fb).flatten()
             self.fallback_trials += int(idx.numel())
@@ -363,7 +376,6 @@ class BatchedBO:
                              (self.y, r.y), (self.n, r.n), (self.best_f, sub.best_f), (self.status, r.status)):
                 dst[idx] = src
             self.launches += sub.launches
-        return BOResult(self.yall, self.picked[:, :self.max_iter], self.nit, self.status, self.X, self.y, self.n, None)
 
     @_on_device
     def run(self) -> BOResult:

@@ -272,3 +272,31 @@ def test_persistent_hands_non_positive_pivots_back_to_the_jitter_path(golden, la
     assert torch.equal(per.picked[[1, 4]], full.picked[[1, 4]]) and torch.equal(per.yall[[1, 4]], full.yall[[1, 4]])
     keep = [0, 2, 3, 5]
     assert np.all(st[keep] == 0) and torch.equal(per.picked[keep], full.picked[keep])
+
+
+def test_auto_takes_the_incremental_path_on_a_lattice_too_large_for_shared_memory():
+    """200 x 200 lattice, step 0.5 (BASELINE configs[3]): posterior='auto' = the O(n) incremental update with the state in
+    HBM; same picks as the full recomputation, and a trial whose rank-1 append meets a non-positive pivot (duplicated
+    point, no noise) is re-run through the per-iteration factorisation with psd_safe_cholesky's jitter rule."""
+    from b200bo import engine, ops
+    lat = ops.Lattice(200, 200, 0.0, 0.0, 0.5)
+    pts = lat.points(DEV)
+    ph = pts.cpu().numpy()
+    obj = (50 + 30 * np.sin(ph[:, 0] / 7.0) * np.cos(ph[:, 1] / 11.0) + 0.1 * ph[:, 0]).astype(np.float32)[None, :]
+    rng = np.random.default_rng(2)
+    T, n0, max_iter = 6, 10, 14
+    idx0 = np.stack([rng.choice(40000, n0, replace=False) for _ in range(T)])
+    idx0[3, 9] = idx0[3, 1]                                              # exactly singular K for trial 3
+    X0, y0 = ph[idx0], obj[0][idx0].astype(np.float64)
+    theta = ogp.raw_to_theta(AUTHOR_THETA_RAW)
+    theta = np.array([0.0, theta[1], theta[2], theta[3]])
+    t = lambda a: torch.as_tensor(a, device=DEV)
+    sid = torch.zeros(T, dtype=torch.int32, device=DEV)
+    full = engine.BatchedBO(pts, t(obj), sid, t(X0), t(y0), max_iter, theta=t(theta), tol=-1.0, lattice=lat).run()
+    bo = engine.BatchedBO(pts, t(obj), sid, t(X0), t(y0), max_iter, theta=t(theta), tol=-1.0, lattice=lat, posterior="auto")
+    assert bo.incremental and not bo.persistent
+    res = bo.run()
+    torch.cuda.synchronize()
+    assert bo.fallback_trials == 1
+    assert torch.equal(res.status, full.status) and torch.equal(res.picked, full.picked) and torch.equal(res.yall, full.yall)
+    assert torch.equal(res.nit, full.nit) and torch.equal(res.X, full.X)
