@@ -497,6 +497,13 @@ bo_fixed_loop_kernel(const BoPersistParams p) {
 // The EI prune test reads a per-candidate fp32 key kept in registers from the state pass (no second trip to L2), and
 // every warp fetches the objective value of its own best candidate before the CTA-level arg-max (the winner's value is
 // then already on chip).
+#ifndef KF2_UNROLL
+#define KF2_UNROLL 4          // observations per trip of the look-up loop
+#endif
+#ifndef KF2_SEED_REREAD
+#define KF2_SEED_REREAD 1     // 1: the seed candidate's state is read back from L2 instead of living in four registers
+#endif
+constexpr int kKf2Unroll = KF2_UNROLL;
 constexpr int BP2_HALF = 512;
 constexpr int BP2_WARPS = BP2_HALF / 32;
 constexpr int BP2_C = 2 * BP_C;          // candidate rows per thread
@@ -719,7 +726,9 @@ bo_fixed_loop2_kernel(const BoPersistParams p) {
           float key[BP2_C];                                            // EI prune keys (registers)
           float seed_u = -INFINITY;
           int seed_c = -1;
+#if !KF2_SEED_REREAD
           double seed_mu = 0.0, seed_ss = 0.0;
+#endif
 #pragma unroll
           for (int pass = 0; pass < 2; ++pass) {
             double v[BP_C];
@@ -728,7 +737,7 @@ bo_fixed_loop2_kernel(const BoPersistParams p) {
             if (active) {
               const unsigned tb32 = smem_u32(table);                   // shared-window address of the table
               const int erow = (ph + pass * BP_C * P) * rowbytes;      // byte offset of the pass's first row
-#pragma unroll 2
+#pragma unroll kKf2Unroll
               for (int j = 0; j <= m; ++j) {
                 const int4 o = *reinterpret_cast<const int4*>(&obs[j]);   // {w.lo, w.hi, cy * rowbytes, cx}
                 const double ow = __hiloint2double(o.y, o.x);
@@ -764,7 +773,11 @@ bo_fixed_loop2_kernel(const BoPersistParams p) {
                     const float vf = fmaxf((float)(sc - ss), (float)p.var_floor);
                     const float rv = __frcp_rn(vf);
                     const float u = df * sqrtf(rv);
+#if KF2_SEED_REREAD
+                    if (u > seed_u) { seed_u = u; seed_c = cc; }
+#else
                     if (u > seed_u) { seed_u = u; seed_c = cc; seed_mu = mu; seed_ss = ss; }
+#endif
                     if (df < 0.0f) {
                       const float u2 = df * df * rv;
                       float corr = 0.5f * __logf(vf);
@@ -786,8 +799,11 @@ bo_fixed_loop2_kernel(const BoPersistParams p) {
           unsigned long long n_eval = 0, n_batch = 0;
           if (ei_prune) {
             if (seed_c >= 0) {                                         // an ATTAINED threshold for the whole trial
-              const double aq = acquisition<B200BO_ACQ_EI>(cst + seed_mu, sc - seed_ss, best, p.acq_param, p.var_floor);
               const int g = g0 + seed_c * gstep;
+#if KF2_SEED_REREAD
+              const double seed_mu = mu_s[g], seed_ss = ss_s[g];
+#endif
+              const double aq = acquisition<B200BO_ACQ_EI>(cst + seed_mu, sc - seed_ss, best, p.acq_param, p.var_floor);
               if (isnan(aq) || aq == INFINITY) flags |= B200BO_ST_NONFINITE;
               if (!isnan(aq)) { best_v = aq; best_i = g; }
               surv &= ~(1u << seed_c);
