@@ -58,6 +58,22 @@ elif what == "kf":
     bo = engine.BatchedBO(pts, obj, sid, pts[idx], obj[sid.long()[:, None], idx].double(), 100, theta=theta, tol=-1.0, lattice=lat,
                           check_every=0, posterior="persistent")
     bo.run()
+elif what == "fit":
+    # the fused hyper-parameter fit (K-C) on T trials of N observations (env T, N): one launch
+    T, n = int(os.environ.get("T", 296)), int(os.environ.get("N", 110))
+    gen = objectives.objectives()
+    surf = gen.wildcatwells_batch([0, 1, 2, 3], [0.2, 0.4, 0.6, 0.8], [0.2, 0.4, 0.6, 0.8], device=dev)
+    obj = surf[:, :100, :100].reshape(4, -1).double()
+    idx = torch.as_tensor(np.stack([rng.choice(10000, n, replace=False) for _ in range(T)]), device=dev)
+    X = pts[idx].contiguous()
+    y = obj[torch.arange(T, device=dev) % 4][torch.arange(T, device=dev)[:, None], idx].contiguous()
+    nn = torch.full((T,), n, dtype=torch.int32, device=dev)
+    ft = fit.LBFGSFitter(T, dev)
+    th = torch.zeros((T, 4), dtype=torch.float64, device=dev)
+    for _ in range(2):
+        ft.fit_into(X, y, nn, 3, th, n_hint=n)
+    torch.cuda.synchronize()
+    print("evals mean / max", float(ft.iters[:, 1].float().mean()), int(ft.iters[:, 1].max()))
 elif what == "rank":
     z = torch.as_tensor(rng.normal(size=10_000_000), device=dev)
     for _ in range(2):
