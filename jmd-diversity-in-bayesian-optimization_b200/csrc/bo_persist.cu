@@ -506,7 +506,12 @@ bo_fixed_loop_kernel(const BoPersistParams p) {
 constexpr int kKf2Unroll = KF2_UNROLL;
 constexpr int BP2_HALF = 512;
 constexpr int BP2_WARPS = BP2_HALF / 32;
-constexpr int BP2_C = 2 * BP_C;          // candidate rows per thread
+#ifndef KF2_PASSES
+#define KF2_PASSES 2          // the 20 rows of a thread are folded in this many passes (rows per pass in registers)
+#endif
+constexpr int BP2_PASSES = KF2_PASSES;
+constexpr int BP2_RP = (2 * BP_C) / BP2_PASSES;   // rows per pass
+constexpr int BP2_C = BP2_RP * BP2_PASSES;        // candidate rows per thread (20)
 
 struct Bp2Smem {
   size_t table, half0, W, obs, kv, lv, yv, mask, stack, red_val, red_idx, red_obj, ctl, thr, half_bytes, total;
@@ -730,13 +735,13 @@ bo_fixed_loop2_kernel(const BoPersistParams p) {
           double seed_mu = 0.0, seed_ss = 0.0;
 #endif
 #pragma unroll
-          for (int pass = 0; pass < 2; ++pass) {
-            double v[BP_C];
+          for (int pass = 0; pass < BP2_PASSES; ++pass) {
+            double v[BP2_RP];
 #pragma unroll
-            for (int c = 0; c < BP_C; ++c) v[c] = 0.0;
+            for (int c = 0; c < BP2_RP; ++c) v[c] = 0.0;
             if (active) {
               const unsigned tb32 = smem_u32(table);                   // shared-window address of the table
-              const int erow = (ph + pass * BP_C * P) * rowbytes;      // byte offset of the pass's first row
+              const int erow = (ph + pass * BP2_RP * P) * rowbytes;    // byte offset of the pass's first row
 #pragma unroll kKf2Unroll
               for (int j = 0; j <= m; ++j) {
                 const int4 o = *reinterpret_cast<const int4*>(&obs[j]);   // {w.lo, w.hi, cy * rowbytes, cx}
@@ -744,7 +749,7 @@ bo_fixed_loop2_kernel(const BoPersistParams p) {
                 const unsigned a0 = tb32 + (unsigned)(abs(gx - o.w) * 8);
                 const int e = o.z - erow;                              // (cy - first row) * rowbytes
 #pragma unroll
-                for (int c = 0; c < BP_C; ++c) {
+                for (int c = 0; c < BP2_RP; ++c) {
                   double kval;                                         // table[|row_c - cy|][|gx - cx|]: VABSDIFF + LDS.64
                   asm("ld.shared.f64 %0, [%1];" : "=d"(kval) : "r"(__sad(e, c * cstride, a0)));
                   v[c] = fma(ow, kval, v[c]);
@@ -752,8 +757,8 @@ bo_fixed_loop2_kernel(const BoPersistParams p) {
               }
             }
 #pragma unroll
-            for (int c = 0; c < BP_C; ++c) {
-              const int cc = pass * BP_C + c;
+            for (int c = 0; c < BP2_RP; ++c) {
+              const int cc = pass * BP2_RP + c;
               const bool live = active && (ph + cc * P) < Gy;
               const int g = g0 + cc * gstep;
               double mu = 0.0, ss = 0.0;

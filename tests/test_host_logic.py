@@ -241,3 +241,28 @@ def test_hp_series_updateres_fills_failed_fits():
         s.data.append(r)
     s.updateres()
     assert s.data["a"].tolist() == [1.0, 1.0, 3.0, 3.0, 3.0] and s.getkeys() == ["a", "b"]
+
+
+def test_window_draw_consumes_the_generator_like_the_reference():
+    """data_gen._pick draws r = Generator.choice(len(possible), 1) and lets the device find the r-th free rank of the
+    window; the reference draws Generator.choice(list(possible), 1) over possible = np.setdiff1d(window, acquired)
+    (Src/data_gen.py:445-466). Same stream position, same element — also after many draws and with acquired ranks
+    inside and outside the window."""
+    a, b = np.random.default_rng(123), np.random.default_rng(123)
+    acquired_a, acquired_b = [7, 9999], [7, 9999]
+    for pct in [5, 95, 5, 50, 95, 2.5, 97.5, 50, 5] * 6:
+        if 2.5 < pct < 97.5:
+            lo, hi = int((pct - 2.5) / 100 * 10000), int(pct / 100 * 10000)
+        elif pct > 97.5:
+            lo, hi = int(95 / 100 * 10000), 10000
+        else:
+            lo, hi = 0, int(5 / 100 * 10000)
+        possible = np.setdiff1d(list(range(lo, hi)), acquired_a)
+        loc_ref = a.choice(list(possible), 1)[0]                       # the reference's draw
+        acquired_a.append(loc_ref)
+        free = (hi - lo) - len({int(x) for x in acquired_b if lo <= x < hi})
+        r = int(b.choice(free, 1)[0])                                  # the engine's draw
+        loc = np.setdiff1d(np.arange(lo, hi), acquired_b)[r]           # what window_pick_kernel returns for r
+        acquired_b.append(loc)
+        assert loc == loc_ref
+    assert a.integers(0, 1 << 30) == b.integers(0, 1 << 30)            # both generators are at the same position
