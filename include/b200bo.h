@@ -291,6 +291,13 @@ int b200bo_gp_fit(const double* X, const double* y, const int32_t* n, const doub
                   double* theta_out, double* raw_out, double* mll_out, int32_t* iters_out, int32_t* status, int T,
                   int n_max, int n_hint, int kernel_id, double lb_noise, double gtol, double ftol, int max_iter,
                   int max_ls, int max_rounds, void* stream);
+/* the same with a launch order: order (T) int32 = a permutation of the trials, CTA b fits trial order[b] (NULL = identity).
+ * CTAs start in that order, so sorting by expected evaluation count, longest first (e.g. the counts of the previous
+ * iteration's fit), ends the launch with its shortest fits. Results do not depend on it. */
+int b200bo_gp_fit_ordered(const double* X, const double* y, const int32_t* n, const double* raw0, int raw0_per_trial,
+                          double* theta_out, double* raw_out, double* mll_out, int32_t* iters_out, int32_t* status, int T,
+                          int n_max, int n_hint, int kernel_id, double lb_noise, double gtol, double ftol, int max_iter,
+                          int max_ls, int max_rounds, const int32_t* order, void* stream);
 
 /* ---- K-C for large training sets -------------------------------------
  * replaces fit_gpytorch_model on the 1 010 ... 1 209-point models of the hyper-parameter extraction experiment

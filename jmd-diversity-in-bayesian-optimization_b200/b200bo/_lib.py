@@ -66,6 +66,8 @@ PROTOTYPES = {
     "b200bo_lbfgs_step": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_double, c_double, c_double, c_int, c_int, P]),
     "b200bo_gp_fit": (c_int, [P, P, P, P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int, c_double, c_double, c_double,
                               c_int, c_int, c_int, P]),
+    "b200bo_gp_fit_ordered": (c_int, [P, P, P, P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int, c_double, c_double, c_double,
+                                      c_int, c_int, c_int, P, P]),
     "b200bo_gp_fit_large_workspace_bytes": (c_size_t, [c_int, c_int]),
     "b200bo_gp_fit_large": (c_int, [P, P, P, P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_double, c_double, c_double,
                                     c_int, c_int, c_int, P, c_size_t, P]),

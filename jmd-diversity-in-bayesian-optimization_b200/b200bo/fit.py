@@ -38,6 +38,7 @@ class LBFGSFitter:
         self.last_launches = 0
         self.last_rounds = 0
         self.fused = bool(fused)
+        self.lpt = True            # launch the fused fit longest-expected-first (b200bo_gp_fit_ordered)
         # optional accounting (bench.py): algorithmic flops of the evaluations run so far, n^3 + 6 n^2 each
         self.account = False
         self.flops = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -54,11 +55,17 @@ class LBFGSFitter:
         T = self.T
         if self.fused:
             # one launch: every trial runs its own L-BFGS to convergence inside its CTA (csrc/gp_fit.cu:gp_fit_sweep_kernel)
-            check(lib.b200bo_gp_fit(p(X), p(y), p(n), p(self.raw0), self.raw0_per_trial, p(theta_out), p(self.raw),
-                                    p(self.mll), p(self.iters), p(status if status is not None else self.kc_status), T,
-                                    y.shape[1], int(n_hint), int(kernel_id), NOISE_LB, self.gtol, self.ftol, self.max_iter,
-                                    self.max_ls, self.max_rounds, s), "gp_fit")
-            self.last_launches = 1
+            # longest expected fit first (the evaluation counts of this trial's previous fit predict the next one's): the
+            # launch then ends with its shortest fits instead of idling on a long one that started late
+            order = None
+            if self.lpt:
+                order = torch.argsort(torch.where(n > 0, self.iters[:, 1], torch.zeros_like(self.iters[:, 1])),
+                                      descending=True, stable=True).to(torch.int32)
+            check(lib.b200bo_gp_fit_ordered(p(X), p(y), p(n), p(self.raw0), self.raw0_per_trial, p(theta_out), p(self.raw),
+                                            p(self.mll), p(self.iters), p(status if status is not None else self.kc_status),
+                                            T, y.shape[1], int(n_hint), int(kernel_id), NOISE_LB, self.gtol, self.ftol,
+                                            self.max_iter, self.max_ls, self.max_rounds, p(order), s), "gp_fit")
+            self.last_launches = 1 + (2 if order is not None else 0)
             self.last_rounds = 0
             if self.account:
                 nf = n.clamp(min=0).double()

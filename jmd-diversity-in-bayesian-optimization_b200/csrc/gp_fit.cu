@@ -407,9 +407,12 @@ __global__ void __launch_bounds__(OW * OW, (OW == 8 ? 1 : (NB <= 6 ? 3 : (NB <= 
 gp_fit_sweep_kernel(const double* __restrict__ X, const double* __restrict__ y, const int32_t* __restrict__ n_arr,
                     const double* __restrict__ raw0, int raw0_per_trial, double* __restrict__ theta_out,
                     double* __restrict__ raw_out, double* __restrict__ mll_out, int32_t* __restrict__ iters_out,
-                    int32_t* __restrict__ status, int n_max, int kernel_id, LbfgsOpts o, int max_rounds) {
+                    int32_t* __restrict__ status, int n_max, int kernel_id, LbfgsOpts o, int max_rounds,
+                    const int32_t* __restrict__ order) {
   extern __shared__ double sm[];
-  const int t = blockIdx.x;
+  // CTAs are handed out in blockIdx order: with `order` (trials sorted by expected evaluation count, longest first) the
+  // launch ends with its shortest fits instead of waiting for a long one that started late
+  const int t = order ? order[blockIdx.x] : blockIdx.x;
   const int n = n_arr[t];
   if (n <= 0) return;
   if (n > OW * NB - 1) {
@@ -473,12 +476,12 @@ static int launch_mll(const double* X, const double* y, const int32_t* n, const 
 template <int NB, int OW>
 static int launch_fit(const double* X, const double* y, const int32_t* n, const double* raw0, int raw0_per_trial,
                       double* theta_out, double* raw_out, double* mll_out, int32_t* iters_out, int32_t* status, int T,
-                      int n_max, int kernel_id, const LbfgsOpts& o, int max_rounds, cudaStream_t st) {
+                      int n_max, int kernel_id, const LbfgsOpts& o, int max_rounds, const int32_t* order, cudaStream_t st) {
   const size_t smem = fit_smem_doubles<NB, OW>() * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(gp_fit_sweep_kernel<NB, OW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e, "gp_fit: smem attribute");
   gp_fit_sweep_kernel<NB, OW><<<T, OW * OW, smem, st>>>(X, y, n, raw0, raw0_per_trial, theta_out, raw_out, mll_out, iters_out,
-                                               status, n_max, kernel_id, o, max_rounds);
+                                               status, n_max, kernel_id, o, max_rounds, order);
   B200BO_CHECK_LAUNCH("gp_fit");
   return 0;
 }
@@ -494,6 +497,14 @@ int b200bo_gp_fit(const double* X, const double* y, const int32_t* n, const doub
                   double* theta_out, double* raw_out, double* mll_out, int32_t* iters_out, int32_t* status, int T,
                   int n_max, int n_hint, int kernel_id, double lb_noise, double gtol, double ftol, int max_iter,
                   int max_ls, int max_rounds, void* stream) {
+  return b200bo_gp_fit_ordered(X, y, n, raw0, raw0_per_trial, theta_out, raw_out, mll_out, iters_out, status, T, n_max,
+                               n_hint, kernel_id, lb_noise, gtol, ftol, max_iter, max_ls, max_rounds, nullptr, stream);
+}
+
+int b200bo_gp_fit_ordered(const double* X, const double* y, const int32_t* n, const double* raw0, int raw0_per_trial,
+                          double* theta_out, double* raw_out, double* mll_out, int32_t* iters_out, int32_t* status, int T,
+                          int n_max, int n_hint, int kernel_id, double lb_noise, double gtol, double ftol, int max_iter,
+                          int max_ls, int max_rounds, const int32_t* order, void* stream) {
   using namespace b200bo;
   if (T < 0 || n_max < 1 || n_max > B200BO_NMAX) return arg_error("gp_fit: T=%d n_max=%d (max %d)", T, n_max, B200BO_NMAX);
   if (kernel_id < 0 || kernel_id > 3) return arg_error("gp_fit: kernel_id=%d", kernel_id);
@@ -505,7 +516,7 @@ int b200bo_gp_fit(const double* X, const double* y, const int32_t* n, const doub
   cudaStream_t st = as_stream(stream);
 #define B200BO_FIT_CASE(ID, NB, OW) \
   case ID: return launch_fit<NB, OW>(X, y, n, raw0, raw0_per_trial, theta_out, raw_out, mll_out, iters_out, status, T, \
-                                     n_max, kernel_id, o, max_rounds, st);
+                                     n_max, kernel_id, o, max_rounds, order, st);
   switch (variant_for(n_cap)) {
     B200BO_FIT_CASE(1, 1, 8) B200BO_FIT_CASE(2, 2, 8) B200BO_FIT_CASE(3, 3, 8) B200BO_FIT_CASE(4, 4, 8)
     B200BO_FIT_CASE(5, 5, 8) B200BO_FIT_CASE(6, 6, 8) B200BO_FIT_CASE(7, 7, 8) B200BO_FIT_CASE(8, 8, 8)

@@ -1,0 +1,23 @@
+"""configs[2] (1 000 trials, fit before every acquisition, tol disabled) by number of concurrent groups (development aid)."""
+import json, os, sys, time
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "jmd-diversity-in-bayesian-optimization_b200")); sys.path.insert(0, ROOT)
+import BO, objectives
+from b200bo import ops
+dev = "cuda:0"
+gen = objectives.objectives()
+S, T = 64, int(os.environ.get("T", 1000))
+surf = gen.wildcatwells_batch(list(range(S)), [0.2] * S, [0.2] * S, device=dev)
+obj = surf[:, :100, :100].reshape(S, -1).contiguous()
+rng = np.random.default_rng(0)
+lat = ops.Lattice(100, 100); pts = lat.points(dev)
+idx = torch.as_tensor(np.stack([rng.choice(10000, 10, replace=False) for _ in range(T)]), device=dev)
+sid = (torch.arange(T, device=dev) % S).int()
+X0 = pts[idx]; y0 = obj[sid.long()[:, None], idx].double()
+for g in [int(v) for v in os.environ.get("GROUPS", "1,3,6,10").split(",")]:
+    for rep in range(2):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        r = BO.BOloop_batched(obj, sid, X0, y0, 100, theta=None, tol=-1.0, device=dev, groups=g)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    print(json.dumps({"groups": g, "seconds": round(dt, 4), "bo_it_per_s": round(int(r.nit.sum()) / dt)}), flush=True)
