@@ -291,11 +291,6 @@ int b200bo_gp_fit(const double* X, const double* y, const int32_t* n, const doub
                   double* theta_out, double* raw_out, double* mll_out, int32_t* iters_out, int32_t* status, int T,
                   int n_max, int n_hint, int kernel_id, double lb_noise, double gtol, double ftol, int max_iter,
                   int max_ls, int max_rounds, void* stream);
-/* the same evaluation on the FP64 MMA path (csrc/gp_fit.cu: sweep blocked by 8 pivots, matrix in DMMA accumulator
- * fragments) for 65 <= n <= 120 — what b200bo_gp_fit takes in that range (B200BO_KC_MMA=0: register-tiled kernel). Same
- * arguments and results as b200bo_mll_value_grad up to the association of the sums (1e-12 relative). */
-int b200bo_mll_value_grad_mma(const double* X, const double* y, const int32_t* n, const double* raw, double* value,
-                              double* grad, int32_t* status, int T, int n_max, int n_hint, int kernel_id, void* stream);
 /* the same with a launch order: order (T) int32 = a permutation of the trials, CTA b fits trial order[b] (NULL = identity).
  * CTAs start in that order, so sorting by expected evaluation count, longest first (e.g. the counts of the previous
  * iteration's fit), ends the launch with its shortest fits. Results do not depend on it. */

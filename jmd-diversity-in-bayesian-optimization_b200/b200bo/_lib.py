@@ -61,7 +61,6 @@ PROTOTYPES = {
                                      P, P, P, c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_double, P,
                                      c_size_t, P]),
     "b200bo_mll_value_grad": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
-    "b200bo_mll_value_grad_mma": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "b200bo_lbfgs_state_bytes": (c_size_t, [c_int]),
     "b200bo_lbfgs_init": (c_int, [P, P, P, c_int, P, P, c_int, c_double, P]),
     "b200bo_lbfgs_step": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_double, c_double, c_double, c_int, c_int, P]),

@@ -6,6 +6,8 @@ still need evaluations, and the host polls it every ``poll`` rounds only to stop
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib, ops
@@ -38,7 +40,7 @@ class LBFGSFitter:
         self.last_launches = 0
         self.last_rounds = 0
         self.fused = bool(fused)
-        self.lpt = True            # launch the fused fit longest-expected-first (b200bo_gp_fit_ordered)
+        self.lpt = os.environ.get("B200BO_FIT_LPT", "1") != "0"     # launch the fused fit longest-expected-first
         # optional accounting (bench.py): algorithmic flops of the evaluations run so far, n^3 + 6 n^2 each
         self.account = False
         self.flops = torch.zeros(1, dtype=torch.float64, device=dev)

@@ -533,20 +533,6 @@ def mll_value_grad(X, y, n, raw, kernel_id, status=None, n_hint=0, value=None, g
     return value, grad, status
 
 
-def mll_value_grad_mma(X, y, n, raw, kernel_id, status=None, n_hint=0):
-    """K-C on the FP64 MMA path (65 <= n <= 120): same arguments and results as mll_value_grad."""
-    lib = _lib.load()
-    _cu(X, torch.float64, "X"); _cu(y, torch.float64, "y"); _cu(n, torch.int32, "n"); _cu(raw, torch.float64, "raw")
-    T, n_max = y.shape
-    value = torch.empty(T, dtype=torch.float64, device=X.device)
-    grad = torch.empty((T, 4), dtype=torch.float64, device=X.device)
-    if status is None:
-        status = torch.zeros(T, dtype=torch.int32, device=X.device)
-    check(lib.b200bo_mll_value_grad_mma(_ptr(X), _ptr(y), _ptr(n), _ptr(raw), _ptr(value), _ptr(grad), _ptr(status), T, n_max,
-                                        int(n_hint), int(kernel_id), _stream()), "mll_value_grad_mma")
-    return value, grad, status
-
-
 # ------------------------------------------------------------------ K-B
 
 def grid_acq_workspace(T: int, G: int, device) -> torch.Tensor:

@@ -486,482 +486,6 @@ static int launch_fit(const double* X, const double* y, const int32_t* n, const 
   return 0;
 }
 
-// =====================================================================================================================
-// K-C on the FP64 MMA path (n = 65 ... 120): the same symmetric sweep, blocked by 8 pivots, the matrix in DMMA
-// accumulator fragments.
-//
-// The register-tiled kernel above pays one barrier and one pivot-column exchange per pivot — 111 dependent steps of 28
-// FMAs per thread at n = 110, with 4 warps per scheduler (ncu: FP64 pipe 32 %, issue slots 48 %,
-// profiles/r2_gp_fit_n110_ncu_full.json). Here a block step sweeps 8 pivots at once:
-//     S = D^-1 (D = A[K,K]),
-//     N_i = A[i,K] S,   A_ij -= N_i A[j,K]^T  (i, j outside K),   A[i,K] = N_i,   A[K,j] = S A[j,K]^T,   A[K,K] = -S
-// — what 8 consecutive single-pivot sweeps compose to. The augmented matrix [[Khat, r], [r^T, 0]] is cut into 8 x 8
-// tiles: Khat padded with the identity to NTK = ceil(n / 8) tile rows (a padding pivot is 1 and couples to nothing),
-// the augmented row r = y - c alone in tile row NTK (never a pivot block). Warp w owns tile rows w and NT-1-w of the
-// lower triangle (NT + 1 tiles, balanced) as mma.sync.m8n8k4.f64 accumulator fragments for the whole evaluation; a
-// block step publishes the pivot column A[.,K] (one 8 x 8 tile per tile row, double-buffered: ONE barrier per step,
-// NTK <= 15 per evaluation instead of n) while the owner of the pivot tile sweeps it in registers (shuffles only) and
-// publishes S; then each warp forms N_i for its two rows with two DMMAs, turns the accumulator
-// fragment into an A fragment with shuffles, and updates its tiles with two DMMAs each (B fragments of A[j,K] from
-// shared memory, 2 LDS.64 per tile). The transcendental code stays in runtime loops staged through shared memory
-// (code size); the distances of the owned entries are cached once per fit (111 KB per CTA at n = 120: two CTAs per SM).
-// Same value / gradient as the kernel above up to the association of the sums (1e-12 relative; tests vs the oracle; the
-// optimiser takes the same path: identical evaluation counts on every probe).
-// Measured (round 2): NOT the hoped-for multiple. One evaluation at n = 110 costs 165 k cycles per CTA either way; phase
-// clocks of this kernel: assembly 7.5 k, the 14 block steps 109 k (7.8 k each), traces 13.8 k, final reduction 12 k.
-// The block step is bound by the 8 dependent pivots of the in-register pivot-tile sweep — a scalar FP64 chain that queues
-// behind the other warps' DMMAs on the same FP64 pipe — not by the 300 DMMAs of the update (FP64 pipe 8 % busy, ncu).
-// A look-ahead sweep (pivot tile of step K+1 swept at the end of step K) and a reciprocal without the IEEE division's
-// special cases were tried: slower (the owner warp stays the straggler). The kernel wins where the register-tiled one
-// loses occupancy: -7 ... -17 % at n = 72 ... 88, -11 ... -25 % at n = 105 ... 120; b200bo_gp_fit dispatches by band.
-constexpr int FM_LD = 12;                 // tile leading dimension in shared memory: fragment loads conflict-free
-constexpr int FM_TILE = 8 * FM_LD;
-constexpr int FM_CH = 4;                  // staging slots per chunk
-
-__host__ __device__ constexpr int fm_warps(int NT) { return (NT + 1) / 2; }
-__host__ __device__ constexpr int fm_threads(int NT) { return 32 * fm_warps(NT); }
-__host__ __device__ constexpr size_t fm_smem_doubles(int NT) {
-  // published pivot columns + S (double buffered) | staging | distance cache | xs ys yv alpha dpiv | scalars
-  return (size_t)2 * (NT + 1) * FM_TILE + (size_t)FM_CH * fm_threads(NT) + (size_t)2 * (NT + 1) * fm_threads(NT) +
-         5 * (size_t)(8 * NT) + 16;
-}
-
-__device__ __forceinline__ void fm_dmma(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
-}
-
-// accumulator fragment (row g = lane / 4, columns 2t, 2t + 1, t = lane % 4) -> A fragments of the same 8 x 8 matrix
-// (row g, column t + 4 s, s = 0, 1)
-__device__ __forceinline__ void fm_c_to_a(double v0, double v1, int lane, double& a0, double& a1) {
-  const int g4 = lane & ~3, t = lane & 3;
-  const int s0 = g4 | (t >> 1), s1 = g4 | ((t + 4) >> 1);
-  const double x0 = __shfl_sync(0xffffffffu, v0, s0), x1 = __shfl_sync(0xffffffffu, v1, s0);
-  const double y0 = __shfl_sync(0xffffffffu, v0, s1), y1 = __shfl_sync(0xffffffffu, v1, s1);
-  a0 = (t & 1) ? x1 : x0;
-  a1 = (t & 1) ? y1 : y0;
-}
-
-// full symmetric sweep of an 8 x 8 block held as an accumulator fragment: (v0, v1) <- -D^-1. Pivots to piv[0..7];
-// returns false when a pivot is not positive. Every lane of the warp takes part (shuffles).
-__device__ __forceinline__ bool fm_sweep8(double& v0, double& v1, int lane, double* piv_out) {
-  const int g = lane >> 2, t = lane & 3;
-  bool ok = true;
-#pragma unroll
-  for (int p = 0; p < 8; ++p) {
-    // column p of the block at this lane's row g, row p at this lane's two columns
-    const double cg0 = __shfl_sync(0xffffffffu, v0, (g << 2) | (p >> 1));
-    const double cg1 = __shfl_sync(0xffffffffu, v1, (g << 2) | (p >> 1));
-    const double colv = (p & 1) ? cg1 : cg0;                            // M[g][p]
-    const double r0 = __shfl_sync(0xffffffffu, v0, (p << 2) | t);       // M[p][2t]
-    const double r1 = __shfl_sync(0xffffffffu, v1, (p << 2) | t);       // M[p][2t + 1]
-    const double d0 = __shfl_sync(0xffffffffu, v0, (p << 2) | (p >> 1));
-    const double d1 = __shfl_sync(0xffffffffu, v1, (p << 2) | (p >> 1));
-    const double d = (p & 1) ? d1 : d0;                                 // M[p][p]
-    if (lane == 0) piv_out[p] = d;
-    ok = ok && d > 0.0;
-    const double inv = 1.0 / d;
-    const double u0 = r0 * inv, u1 = r1 * inv;
-    double n0 = fma(-colv, u0, v0), n1 = fma(-colv, u1, v1);
-    if (2 * t == p) n0 = colv * inv;                                    // pivot column: v / d
-    if (2 * t + 1 == p) n1 = colv * inv;
-    if (g == p) {                                                       // pivot row: v / d, pivot itself -1 / d
-      n0 = (2 * t == p) ? -inv : u0;
-      n1 = (2 * t + 1 == p) ? -inv : u1;
-    }
-    v0 = n0;
-    v1 = n1;
-  }
-  return ok;
-}
-
-struct FmSmem {
-  double* pO;      // 2 x (NT + 1) x FM_TILE: published pivot columns, tile NT = S = D^-1 (double buffered)
-  double* kbuf;    // FM_CH x threads staging
-  double* dist;    // 2 (NT + 1) x threads: distance (RBF: squared distance) of every owned entry, [slot][thread]
-  double* xs;      // 8 NT
-  double* ys;
-  double* yv;
-  double* alpha;   // 8 NT (alpha[c] = (Khat^-1 r)_c)
-  double* dpiv;    // 8 NT pivots
-  double* misc;    // [0] = -r^T Khat^-1 r
-};
-
-template <int NT>
-__device__ __forceinline__ FmSmem fm_carve(double* sm) {
-  FmSmem s;
-  s.pO = sm;
-  s.kbuf = s.pO + 2 * (NT + 1) * FM_TILE;
-  s.dist = s.kbuf + FM_CH * fm_threads(NT);
-  s.xs = s.dist + 2 * (NT + 1) * fm_threads(NT);
-  s.ys = s.xs + 8 * NT;
-  s.yv = s.ys + 8 * NT;
-  s.alpha = s.yv + 8 * NT;
-  s.dpiv = s.alpha + 8 * NT;
-  s.misc = s.dpiv + 8 * NT;
-  return s;
-}
-
-// tile jj (0 .. NT) of warp w: rows ra = w (tiles jj = 0 .. ra) and rb = NT-1-w (tiles jj = ra+1 .. NT); the middle warp
-// of an odd NT owns one row only (its second half is dead)
-template <int NT>
-__device__ __forceinline__ bool fm_tile_of(int warp, int jj, int& ti, int& tj) {
-  const int ra = warp, rb = NT - 1 - warp;
-  if (jj <= ra) { ti = ra; tj = jj; return true; }
-  ti = rb; tj = jj - ra - 1;
-  return rb > ra;
-}
-
-template <int NT>
-__device__ __forceinline__ void mll_eval_mma(const FmSmem& s, int n, int kernel_id, const FitPar* par, double* red, double* out,
-                                             int* st_out) {
-  constexpr int NTH = fm_threads(NT), NTK = NT - 1, NTL = NT + 1, NSL = 2 * NTL;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  const double noise = par->noise, cst = par->cst, sc = par->sc, ell = par->ell, a_scale = par->a_scale;
-  double C[NTL][2];
-  int st = 0;
-  bool ok = false;
-  for (int attempt = 0; attempt < 4 && !ok; ++attempt) {
-    const double jitter = attempt == 0 ? 0.0 : (attempt == 1 ? 1e-8 : (attempt == 2 ? 1e-7 : 1e-6));
-    if (attempt > 0) st |= B200BO_ST_JITTER;
-    __syncthreads();
-    // ---- assemble the owned tiles (runtime loop over the 2 (NT + 1) entries of a lane, staged in chunks)
-#pragma unroll
-    for (int lo = 0; lo < NSL; lo += FM_CH) {
-      const int hi = lo + FM_CH < NSL ? lo + FM_CH : NSL;
-#pragma unroll 1
-      for (int sl = lo; sl < hi; ++sl) {
-        int ti, tj;
-        const bool live = fm_tile_of<NT>(warp, sl >> 1, ti, tj);
-        const int r = 8 * ti + g, c = 8 * tj + 2 * t + (sl & 1);
-        double v = 0.0;
-        if (live) {
-          if (ti == NTK) {                                  // augmented row: r = y - c in local row 0
-            if (g == 0 && c < n) v = s.yv[c] - cst;
-          } else if (r < n && c < n) {
-            v = kern_only(kernel_id, s.dist[(size_t)sl * NTH + tid], sc, ell, a_scale);
-            if (r == c) v += noise + jitter;
-          } else if (r == c) {
-            v = 1.0;                                        // identity padding of Khat
-          }
-        }
-        s.kbuf[(size_t)(sl - lo) * NTH + tid] = v;
-      }
-#pragma unroll
-      for (int sl = 0; sl < NSL; ++sl)
-        if (sl >= lo && sl < hi) C[sl >> 1][sl & 1] = s.kbuf[(size_t)(sl - lo) * NTH + tid];
-    }
-    // ---- block sweeps K = 0 .. NTK-1
-    ok = true;
-#pragma unroll 1
-    for (int k = 0; k < NTK; ++k) {
-      double* pO = s.pO + (size_t)(k & 1) * (NT + 1) * FM_TILE;
-      double m0 = 0.0, m1 = 0.0;                            // -D^-1 (kept by the owner of the pivot tile)
-      // publish the pivot column A[., K]: tile (i, k) as stored, tile (k, j) (j < k) transposed into slot j
-      bool own_pivot = false;
-#pragma unroll
-      for (int jj = 0; jj < NTL; ++jj) {
-        int ti, tj;
-        if (!fm_tile_of<NT>(warp, jj, ti, tj)) continue;
-        if (tj == k) {
-          *reinterpret_cast<double2*>(pO + (size_t)ti * FM_TILE + g * FM_LD + 2 * t) = make_double2(C[jj][0], C[jj][1]);
-          if (ti == k) { m0 = C[jj][0]; m1 = C[jj][1]; own_pivot = true; }
-        } else if (ti == k) {
-          pO[(size_t)tj * FM_TILE + (2 * t) * FM_LD + g] = C[jj][0];
-          pO[(size_t)tj * FM_TILE + (2 * t + 1) * FM_LD + g] = C[jj][1];
-        }
-      }
-      if (own_pivot) {
-        // the owner of the pivot tile sweeps it while the other warps publish: S = D^-1 to slot NT, pivots to dpiv
-        const bool good = fm_sweep8(m0, m1, lane, s.dpiv + 8 * k);
-        *reinterpret_cast<double2*>(pO + (size_t)NT * FM_TILE + g * FM_LD + 2 * t) = make_double2(-m0, -m1);
-        if (lane == 0) s.misc[1 + (k & 1)] = good ? 1.0 : 0.0;
-      }
-      __syncthreads();
-      if (s.misc[1 + (k & 1)] == 0.0) { ok = false; break; }             // a pivot was not positive (uniform)
-      // S = D^-1 as A fragments (= B fragments: S is symmetric)
-      const double sa0 = pO[(size_t)NT * FM_TILE + g * FM_LD + t], sa1 = pO[(size_t)NT * FM_TILE + g * FM_LD + t + 4];
-      // N_i = A[i,K] S for the warp's two rows (row K itself: "N" := S, used as S A[j,K]^T)
-      double na[2][2], nc[2][2];                            // N_i as A fragments / in the accumulator layout
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int ti = h == 0 ? warp : NT - 1 - warp;
-        nc[h][0] = nc[h][1] = 0.0;
-        if (ti == k) { na[h][0] = sa0; na[h][1] = sa1; continue; }
-        const double* po = pO + (size_t)ti * FM_TILE + g * FM_LD + t;
-        fm_dmma(nc[h][0], nc[h][1], po[0], sa0);
-        fm_dmma(nc[h][0], nc[h][1], po[4], sa1);
-        fm_c_to_a(nc[h][0], nc[h][1], lane, na[h][0], na[h][1]);
-      }
-      // rank-8 update of EVERY owned tile, unconditionally (the tiles of row / column K are overwritten just below):
-      // straight-line DMMA pairs the scheduler can interleave across tiles
-#pragma unroll
-      for (int jj = 0; jj < NTL; ++jj) {
-        int ti, tj;
-        fm_tile_of<NT>(warp, jj, ti, tj);
-        const int h = jj <= warp ? 0 : 1;
-        const double* pb = pO + (size_t)tj * FM_TILE + g * FM_LD + t;
-        fm_dmma(C[jj][0], C[jj][1], -na[h][0], pb[0]);
-        fm_dmma(C[jj][0], C[jj][1], -na[h][1], pb[4]);
-      }
-      // column K: A[i,K] = N_i ; row K: A[K,j] = S A[j,K]^T, A[K,K] = -S
-#pragma unroll
-      for (int jj = 0; jj < NTL; ++jj) {
-        int ti, tj;
-        if (!fm_tile_of<NT>(warp, jj, ti, tj)) continue;
-        const int h = jj <= warp ? 0 : 1;
-        if (ti == k) {
-          if (tj == k) { C[jj][0] = m0; C[jj][1] = m1; continue; }
-          const double* pb = pO + (size_t)tj * FM_TILE + g * FM_LD + t;
-          double c0 = 0.0, c1 = 0.0;
-          fm_dmma(c0, c1, sa0, pb[0]);
-          fm_dmma(c0, c1, sa1, pb[4]);
-          C[jj][0] = c0; C[jj][1] = c1;
-        } else if (tj == k) {
-          C[jj][0] = nc[h][0]; C[jj][1] = nc[h][1];
-        }
-      }
-    }
-  }
-  if (!ok) {
-    if (tid == 0) {
-      *st_out = st | B200BO_ST_CHOL_FAIL;
-      for (int q = 0; q < 5; ++q) out[q] = nan("");
-    }
-    __syncthreads();
-    return;
-  }
-  // ---- alpha = augmented row (tile row NTK, local row 0), quadratic form = -corner
-#pragma unroll
-  for (int jj = 0; jj < NTL; ++jj) {
-    int ti, tj;
-    if (!fm_tile_of<NT>(warp, jj, ti, tj)) continue;
-    if (ti == NTK && g == 0) {
-      if (tj < NTK) {
-        s.alpha[8 * tj + 2 * t] = C[jj][0];
-        s.alpha[8 * tj + 2 * t + 1] = C[jj][1];
-      } else if (t == 0) {
-        s.misc[0] = C[jj][0];
-      }
-    }
-  }
-  __syncthreads();
-  double q1 = 0.0, q2 = 0.0, q3 = 0.0, q4 = 0.0, q5 = 0.0;
-  for (int c = tid; c < n; c += NTH) {
-    q1 += s.alpha[c];
-    q5 += log(s.dpiv[c]);
-  }
-  // ---- traces: A = alpha alpha^T - Khat^-1 against k and dk/dell. Off-diagonal tiles stand for (r,c) and (c,r); a
-  // diagonal tile holds both triangles itself.
-#pragma unroll
-  for (int lo = 0; lo < NSL; lo += FM_CH) {
-    const int hi = lo + FM_CH < NSL ? lo + FM_CH : NSL;
-#pragma unroll
-    for (int sl = 0; sl < NSL; ++sl) {
-      if (sl < lo || sl >= hi) continue;
-      int ti, tj;
-      const bool live = fm_tile_of<NT>(warp, sl >> 1, ti, tj);
-      const int r = 8 * ti + g, c = 8 * tj + 2 * t + (sl & 1);
-      double wa = 0.0;
-      if (live && ti < NTK && r < n && c < n) {
-        const double a_rc = fma(s.alpha[r], s.alpha[c], C[sl >> 1][sl & 1]);
-        if (r == c) q2 += a_rc;
-        wa = (ti == tj) ? a_rc : 2.0 * a_rc;
-      }
-      s.kbuf[(size_t)(sl - lo) * NTH + tid] = wa;
-    }
-#pragma unroll 1
-    for (int sl = lo; sl < hi; ++sl) {
-      int ti, tj;
-      const bool live = fm_tile_of<NT>(warp, sl >> 1, ti, tj);
-      const int r = 8 * ti + g, c = 8 * tj + 2 * t + (sl & 1);
-      if (live && ti < NTK && r < n && c < n) {
-        double kl, dk;
-        kern_pair(kernel_id, s.dist[(size_t)sl * NTH + tid], ell, a_scale, kl, dk);
-        const double wa = s.kbuf[(size_t)(sl - lo) * NTH + tid];
-        q3 = fma(wa, kl, q3);
-        q4 = fma(wa, dk, q4);
-      }
-    }
-  }
-  double q[5] = {q1, q2, q3, q4, q5};
-#pragma unroll
-  for (int m = 0; m < 5; ++m) {
-    const double v = warp_sum(q[m]);
-    if (lane == 0) red[warp * 5 + m] = v;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    double tsum[5];
-    for (int m = 0; m < 5; ++m) {
-      double acc = 0.0;
-      for (int w = 0; w < fm_warps(NT); ++w) acc += red[w * 5 + m];
-      tsum[m] = acc;
-    }
-    const double nn = (double)n;
-    const double quad = -s.misc[0];
-    const double ll = -0.5 * quad - 0.5 * tsum[4] - 0.5 * nn * kLog2Pi;
-    const double a_prior = 1.1, rate = 0.05;
-    const double lp = par->lp_const + (a_prior - 1.0) * log(noise) - rate * noise;
-    out[0] = (ll + lp) / nn;
-    out[1] = (0.5 * tsum[1] + (a_prior - 1.0) / noise - rate) / nn;
-    out[2] = tsum[0] / nn;
-    out[3] = 0.5 * tsum[2] * par->sig_s / nn;
-    out[4] = 0.5 * (tsum[3] * (sc / ell)) * par->sig_l / nn;
-    *st_out = st;
-  }
-  __syncthreads();
-}
-
-template <int NT>
-__device__ __forceinline__ void fm_load_trial(const FmSmem& s, const double* __restrict__ X, const double* __restrict__ y, int t,
-                                              int n, int n_max) {
-  for (int i = threadIdx.x; i < 8 * NT; i += fm_threads(NT)) {
-    const bool live = i < n;
-    s.xs[i] = live ? X[((size_t)t * n_max + i) * 2] : 0.0;
-    s.ys[i] = live ? X[((size_t)t * n_max + i) * 2 + 1] : 0.0;
-    s.yv[i] = live ? y[(size_t)t * n_max + i] : 0.0;
-  }
-  __syncthreads();
-}
-
-// distances of the owned entries, once per fit (they do not depend on the hyper-parameters)
-template <int NT>
-__device__ __forceinline__ void fm_cache_dist(const FmSmem& s, int n, int kernel_id) {
-  constexpr int NTH = fm_threads(NT), NSL = 2 * (NT + 1);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-#pragma unroll 1
-  for (int sl = 0; sl < NSL; ++sl) {
-    int ti, tj;
-    const bool live = fm_tile_of<NT>(warp, sl >> 1, ti, tj);
-    const int r = 8 * ti + g, c = 8 * tj + 2 * t + (sl & 1);
-    double v = 0.0;
-    if (live && r < n && c < n) {
-      const double dx = s.xs[r] - s.xs[c], dy = s.ys[r] - s.ys[c];
-      const double r2 = dx * dx + dy * dy;
-      v = kernel_id == B200BO_KERNEL_RBF ? r2 : sqrt(r2);
-    }
-    s.dist[(size_t)sl * NTH + tid] = v;
-  }
-}
-
-template <int NT>
-__global__ void __launch_bounds__(fm_threads(NT), 2)
-mll_mma_kernel(const double* __restrict__ X, const double* __restrict__ y, const int32_t* __restrict__ n_arr,
-               const double* __restrict__ raw, double* __restrict__ value, double* __restrict__ grad,
-               int32_t* __restrict__ status, int n_max, int kernel_id) {
-  extern __shared__ double sm[];
-  const int t = blockIdx.x;
-  const int n = n_arr[t];
-  if (n <= 0) return;
-  if (n > 8 * (NT - 1)) {
-    if (threadIdx.x == 0 && status) atomicOr(&status[t], B200BO_ST_CHOL_FAIL);
-    return;
-  }
-  const FmSmem s = fm_carve<NT>(sm);
-  __shared__ double red[fm_warps(NT) * 5];
-  __shared__ double out[5];
-  __shared__ FitPar par;
-  __shared__ int sh_st;
-  fm_load_trial<NT>(s, X, y, t, n, n_max);
-  fm_cache_dist<NT>(s, n, kernel_id);
-  if (threadIdx.x == 0) fit_params_from_raw(raw + (size_t)t * 4, kernel_id, gamma_prior_const(), par);
-  __syncthreads();
-  mll_eval_mma<NT>(s, n, kernel_id, &par, red, out, &sh_st);
-  if (threadIdx.x == 0) {
-    value[t] = out[0];
-    for (int q = 0; q < 4; ++q) grad[(size_t)t * 4 + q] = out[1 + q];
-    if (status && sh_st) atomicOr(&status[t], sh_st);
-  }
-}
-
-template <int NT>
-__global__ void __launch_bounds__(fm_threads(NT), 2)
-gp_fit_mma_kernel(const double* __restrict__ X, const double* __restrict__ y, const int32_t* __restrict__ n_arr,
-                  const double* __restrict__ raw0, int raw0_per_trial, double* __restrict__ theta_out,
-                  double* __restrict__ raw_out, double* __restrict__ mll_out, int32_t* __restrict__ iters_out,
-                  int32_t* __restrict__ status, int n_max, int kernel_id, LbfgsOpts o, int max_rounds,
-                  const int32_t* __restrict__ order) {
-  extern __shared__ double sm[];
-  const int t = order ? order[blockIdx.x] : blockIdx.x;
-  const int n = n_arr[t];
-  if (n <= 0) return;
-  if (n > 8 * (NT - 1)) {
-    if (threadIdx.x == 0 && status) atomicOr(&status[t], B200BO_ST_CHOL_FAIL);
-    return;
-  }
-  const FmSmem s = fm_carve<NT>(sm);
-  __shared__ double red[fm_warps(NT) * 5];
-  __shared__ double out[5];
-  __shared__ FitPar par;
-  __shared__ LbfgsState lst;
-  __shared__ double xt[4];
-  __shared__ int sh_done, sh_st;
-  fm_load_trial<NT>(s, X, y, t, n, n_max);
-  fm_cache_dist<NT>(s, n, kernel_id);
-  if (threadIdx.x == 0) {
-    lst.hist_n = 0; lst.hist_head = 0; lst.iter = 0; lst.ls_iter = 0; lst.nfev = 0; lst.resets = 0; lst.phase = 0;
-    for (int i = 0; i < 4; ++i) xt[i] = raw0[raw0_per_trial ? (size_t)t * 4 + i : i];
-    xt[0] = fmax(xt[0], o.lb_noise);
-    fit_params_from_raw(xt, kernel_id, gamma_prior_const(), par);
-    sh_done = 0;
-    sh_st = 0;
-  }
-  __syncthreads();
-  for (int round = 0; round <= max_rounds; ++round) {
-    mll_eval_mma<NT>(s, n, kernel_id, &par, red, out, &sh_st);
-    if (threadIdx.x == 0) {
-      LbfgsOpts oo = o;
-      if (round == max_rounds) oo.max_ls = -1;
-      double gt[4];
-      for (int i = 0; i < 4; ++i) gt[i] = -out[1 + i];
-      sh_done = lbfgs_advance(lst, oo, xt, -out[0], gt) ? 1 : 0;
-      if (!sh_done) fit_params_from_raw(xt, kernel_id, par.lp_const, par);
-    }
-    __syncthreads();
-    if (sh_done) break;
-  }
-  if (threadIdx.x == 0) {
-    if (raw_out) for (int i = 0; i < 4; ++i) raw_out[(size_t)t * 4 + i] = lst.x[i];
-    if (theta_out) {
-      theta_out[(size_t)t * 4 + 0] = lst.x[0];
-      theta_out[(size_t)t * 4 + 1] = lst.x[1];
-      theta_out[(size_t)t * 4 + 2] = softplus20(lst.x[2]);
-      theta_out[(size_t)t * 4 + 3] = softplus20(lst.x[3]);
-    }
-    if (mll_out) mll_out[t] = -lst.f;
-    if (iters_out) { iters_out[(size_t)t * 2] = lst.iter; iters_out[(size_t)t * 2 + 1] = lst.nfev; }
-  }
-}
-
-template <int NT>
-static int launch_fit_mma(const double* X, const double* y, const int32_t* n, const double* raw0, int raw0_per_trial,
-                          double* theta_out, double* raw_out, double* mll_out, int32_t* iters_out, int32_t* status, int T,
-                          int n_max, int kernel_id, const LbfgsOpts& o, int max_rounds, const int32_t* order, cudaStream_t st) {
-  const size_t smem = fm_smem_doubles(NT) * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(gp_fit_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return cuda_status(e, "gp_fit: smem attribute");
-  gp_fit_mma_kernel<NT><<<T, fm_threads(NT), smem, st>>>(X, y, n, raw0, raw0_per_trial, theta_out, raw_out, mll_out, iters_out,
-                                                         status, n_max, kernel_id, o, max_rounds, order);
-  B200BO_CHECK_LAUNCH("gp_fit");
-  return 0;
-}
-
-template <int NT>
-static int launch_mll_mma(const double* X, const double* y, const int32_t* n, const double* raw, double* value, double* grad,
-                          int32_t* status, int T, int n_max, int kernel_id, cudaStream_t st) {
-  const size_t smem = fm_smem_doubles(NT) * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(mll_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return cuda_status(e, "mll_value_grad: smem attribute");
-  mll_mma_kernel<NT><<<T, fm_threads(NT), smem, st>>>(X, y, n, raw, value, grad, status, n_max, kernel_id);
-  B200BO_CHECK_LAUNCH("mll_value_grad");
-  return 0;
-}
-
-// tile rows of the MMA variant for n observations: ceil(n / 8) + 1 (augmented row); 0 = not covered (n < 65 or > 120)
-static int fm_nt_for(int n_cap) { return (n_cap >= 65 && n_cap <= 120) ? (n_cap + 7) / 8 + 1 : 0; }
-
 // n observations + the augmented row: variant id = NB for the 8 x 8 grid (<= 64 rows), 100 + NB for 16 x 16
 static int variant_for(int n_cap) { return n_cap + 1 <= 64 ? (n_cap + 1 + 7) / 8 : 100 + (n_cap + 1 + 15) / 16; }
 
@@ -990,20 +514,6 @@ int b200bo_gp_fit_ordered(const double* X, const double* y, const int32_t* n, co
   LbfgsOpts o;
   o.lb_noise = lb_noise; o.gtol = gtol; o.ftol = ftol; o.c1 = 1e-4; o.max_iter = max_iter; o.max_ls = max_ls;
   cudaStream_t st = as_stream(stream);
-  static const int mma_env = [] { const char* e = getenv("B200BO_KC_MMA"); return e ? atoi(e) : 1; }();
-  // measured per band (tools/fit_compare.py, 296 fits): -7 ... -17 % at n = 72 ... 88, -11 ... -25 % at n = 105 ... 120,
-  // +-3 % at n = 89 ... 104 (the register-tiled kernel keeps that band); B200BO_KC_MMA=2 forces the MMA path everywhere
-  if (mma_env == 2 || (mma_env == 1 && (n_cap <= 88 || n_cap >= 105))) {
-#define B200BO_FITM_CASE(NT) \
-  case NT: return launch_fit_mma<NT>(X, y, n, raw0, raw0_per_trial, theta_out, raw_out, mll_out, iters_out, status, T, n_max, \
-                                     kernel_id, o, max_rounds, order, st);
-    switch (fm_nt_for(n_cap)) {
-      B200BO_FITM_CASE(10) B200BO_FITM_CASE(11) B200BO_FITM_CASE(12) B200BO_FITM_CASE(13) B200BO_FITM_CASE(14)
-      B200BO_FITM_CASE(15) B200BO_FITM_CASE(16)
-      default: break;
-    }
-#undef B200BO_FITM_CASE
-  }
 #define B200BO_FIT_CASE(ID, NB, OW) \
   case ID: return launch_fit<NB, OW>(X, y, n, raw0, raw0_per_trial, theta_out, raw_out, mll_out, iters_out, status, T, \
                                      n_max, kernel_id, o, max_rounds, order, st);
@@ -1036,25 +546,6 @@ int b200bo_mll_value_grad(const double* X, const double* y, const int32_t* n, co
   }
 #undef B200BO_MLL_CASE
   return arg_error("mll_value_grad: n=%d unsupported", n_cap);
-}
-
-int b200bo_mll_value_grad_mma(const double* X, const double* y, const int32_t* n, const double* raw, double* value,
-                              double* grad, int32_t* status, int T, int n_max, int n_hint, int kernel_id, void* stream) {
-  using namespace b200bo;
-  if (T < 0 || n_max < 1 || n_max > B200BO_NMAX) return arg_error("mll_value_grad_mma: T=%d n_max=%d", T, n_max);
-  if (kernel_id < 0 || kernel_id > 3) return arg_error("mll_value_grad_mma: kernel_id=%d", kernel_id);
-  if (T == 0) return 0;
-  if (!X || !y || !n || !raw || !value || !grad) return arg_error("mll_value_grad_mma: null pointer");
-  const int n_cap = (n_hint > 0 && n_hint < n_max) ? n_hint : n_max;
-  cudaStream_t st = as_stream(stream);
-#define B200BO_MLLM_CASE(NT) case NT: return launch_mll_mma<NT>(X, y, n, raw, value, grad, status, T, n_max, kernel_id, st);
-  switch (fm_nt_for(n_cap)) {
-    B200BO_MLLM_CASE(10) B200BO_MLLM_CASE(11) B200BO_MLLM_CASE(12) B200BO_MLLM_CASE(13) B200BO_MLLM_CASE(14)
-    B200BO_MLLM_CASE(15) B200BO_MLLM_CASE(16)
-    default: break;
-  }
-#undef B200BO_MLLM_CASE
-  return arg_error("mll_value_grad_mma: n=%d outside 65 ... 120", n_cap);
 }
 
 }  // extern "C"

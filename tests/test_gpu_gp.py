@@ -184,56 +184,6 @@ def test_mll_value_and_gradient(golden, lattice_grid, kid):
 
 
 @pytest.mark.parametrize("kid", [0, 1, 2, 3])
-@pytest.mark.parametrize("n_cap", [65, 72, 73, 88, 97, 110, 120])
-def test_mll_value_and_gradient_mma_path(golden, lattice_grid, kid, n_cap):
-    """K-C on the FP64 MMA path (sweep blocked by 8 pivots, matrix in DMMA accumulator fragments; what b200bo_gp_fit
-    takes for 65 <= n <= 120): value 1e-8 / gradient 1e-7 against the oracle, 1e-10 against the register-tiled kernel,
-    mixed n inside one launch (every tile-row count of the template), the jitter path, status bits."""
-    from b200bo import ops
-    sizes = sorted({n_cap, max(1, n_cap - 1), max(1, n_cap - 7), max(1, n_cap - 8), 66 if n_cap > 66 else 3, 9})
-    T = len(sizes) + 1
-    X, y, n, _ = _make_batch(golden, lattice_grid, T, sizes + [n_cap], n_cap, seed=kid + n_cap)
-    rng = np.random.default_rng(kid + n_cap)
-    raw = np.stack([np.array([rng.uniform(1e-3, 3.0), rng.uniform(0, 50), rng.uniform(-2, 200), rng.uniform(-2, 15)]) for _ in range(T)])
-    raw[0] = ogp.DEFAULT_RAW
-    raw[-1] = [1e-4, 41.8, 190.4, 9.87]                                   # the noise bound, a badly conditioned Khat
-    v, g, st = ops.mll_value_grad_mma(_to(X), _to(y), _to(n), _to(raw), kid, n_hint=n_cap)
-    v2, g2, st2 = ops.mll_value_grad(_to(X), _to(y), _to(n), _to(raw), kid, n_hint=n_cap)
-    torch.cuda.synchronize()
-    assert torch.equal(st, st2)
-    ok = ~torch.isnan(v2)
-    assert torch.allclose(v[ok], v2[ok], rtol=1e-10, atol=0) and torch.allclose(g[ok], g2[ok], rtol=1e-7, atol=1e-9)
-    v = v.cpu().numpy(); g = g.cpu().numpy()
-    for t in range(T):
-        vo, go, so = ogp.mll_value_grad(X[t, :n[t]], y[t, :n[t]], raw[t], kid)
-        assert st[t].item() == so
-        if np.isfinite(vo):
-            assert abs(v[t] - vo) <= 1e-8 * abs(vo), (t, n[t], v[t], vo)
-            assert np.allclose(g[t], go, rtol=1e-7, atol=1e-9 * np.abs(go).max()), (t, n[t], g[t], go)
-
-
-def test_fit_on_the_mma_path_reaches_the_optimum_of_the_register_kernel(golden, lattice_grid, monkeypatch):
-    """The fused fit at n = 70 ... 110 (MMA path) against the same fit with B200BO_KC_MMA=0 semantics (round-based
-    register-tiled evaluations): same optimum (marginal likelihood 1e-9, theta 1e-5), same evaluation counts up to the
-    rounding-level differences of a line search, and bit-identical when repeated."""
-    from b200bo import fit
-    sizes = [70, 80, 96, 104, 110, 110, 72, 88]
-    T = len(sizes)
-    X, y, n, _ = _make_batch(golden, lattice_grid, T, sizes, 110, seed=31)      # n_hint 110: the MMA band
-    outs = []
-    for fused in (True, True, False):
-        f = fit.LBFGSFitter(T, "cuda:0", fused=fused)
-        th = torch.zeros((T, 4), dtype=torch.float64, device="cuda:0")
-        f.fit_into(_to(X), _to(y), _to(n), 3, th, n_hint=110)
-        torch.cuda.synchronize()
-        outs.append((th.clone(), f.mll.clone(), f.iters.clone()))
-    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][2], outs[1][2])      # deterministic
-    assert torch.allclose(outs[0][1], outs[2][1], rtol=1e-9, atol=0)
-    assert torch.allclose(outs[0][0], outs[2][0], rtol=1e-5, atol=1e-8)
-    assert (outs[0][2][:, 1] - outs[2][2][:, 1]).abs().max().item() <= 6
-
-
-@pytest.mark.parametrize("kid", [0, 1, 2, 3])
 def test_lattice_variant_is_bit_identical_to_generic(golden, lattice_grid, kid):
     """Table look-ups replace G*n kernel evaluations on a lattice; values must not change at all."""
     from b200bo import ops
