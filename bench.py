@@ -691,15 +691,16 @@ def bench_dpp(dev):
                                     "permutation back on the host"}
     # roofline of the scorer by SURVEY.md 8(d): 623 flops per set (k = 10; exp / log / sqrt / div = 1 flop) against the
     # FP64 pipe; the slot view counts what the pipe really issues (exp 22, sqrt 15, div 14, log 51 DFMA-slots:
-    # profiles/fp64_peaks_r1.json), i.e. 3045 slots per set for the generic kernel and 870 for the lattice-table variant
+    # profiles/fp64_peaks_r1.json) — with ONE log per set (product of the pivots): 2586 slots per set for the generic
+    # kernel and 411 for the lattice-table variant
     peak = 37.055
     out["roofline"] = {"bound": "fp64 pipe", "flops_per_set": 623, "peak_tflops": peak,
                        "generic": {"achieved_tflops": out["n1e7"]["sets_per_s"] * 623 / 1e12,
                                    "frac": out["n1e7"]["sets_per_s"] * 623 / 1e12 / peak,
-                                   "pipe_slot_frac": out["n1e7"]["sets_per_s"] * 3045 * 2 / 1e12 / peak},
+                                   "pipe_slot_frac": out["n1e7"]["sets_per_s"] * 2586 * 2 / 1e12 / peak},
                        "lattice": {"achieved_tflops": out["lattice_n1e7"]["sets_per_s"] * 623 / 1e12,
                                    "frac": out["lattice_n1e7"]["sets_per_s"] * 623 / 1e12 / peak,
-                                   "pipe_slot_frac": out["lattice_n1e7"]["sets_per_s"] * 870 * 2 / 1e12 / peak},
+                                   "pipe_slot_frac": out["lattice_n1e7"]["sets_per_s"] * 411 * 2 / 1e12 / peak},
                        "hbm_bytes_per_set": 48, "hbm_gbs_lattice": out["lattice_n1e7"]["sets_per_s"] * 48 / 1e9}
     # the reference's generate() path (un-rank + score + rank) at its own size, N = 10 000 (3.22 s in SURVEY.md §6)
     import data_gen

@@ -252,13 +252,13 @@ __device__ __forceinline__ double ldl_logabsdet_unitdiag(const double (&D)[K * (
     for (int c = 0; c < r; ++c) A[r * (r + 1) / 2 + c] = exp(neg_gamma * D[r * (r - 1) / 2 + c]);
     A[r * (r + 1) / 2 + r] = 1.0;
   }
-  double acc = 0.0;
+  double piv[K];                                      // log|det| exactly as ldl_logabsdet (csrc/dpp.cu) forms it
   bool singular = false;
 #pragma unroll
   for (int j = 0; j < K; ++j) {
     const double d = A[j * (j + 1) / 2 + j];
     singular = singular || d == 0.0;
-    acc += log(fabs(d));
+    piv[j] = d;
     const double inv = 1.0 / d;
 #pragma unroll
     for (int c = j + 1; c < K; ++c) {
@@ -267,7 +267,16 @@ __device__ __forceinline__ double ldl_logabsdet_unitdiag(const double (&D)[K * (
       for (int r = c; r < K; ++r) A[r * (r + 1) / 2 + c] = fma(-A[r * (r + 1) / 2 + j], lc, A[r * (r + 1) / 2 + c]);
     }
   }
-  return singular ? -INFINITY : acc;
+  if (singular) return -INFINITY;
+  double p = 1.0;
+#pragma unroll
+  for (int j = 0; j < K; ++j) p *= piv[j];
+  p = fabs(p);
+  if (p > 1e-250 && p < 1e250) return log(p);
+  double acc = 0.0;
+#pragma unroll 1
+  for (int j = 0; j < K; ++j) acc += log(fabs(piv[j]));
+  return acc;
 }
 
 template <int K>
