@@ -1,4 +1,5 @@
-"""BASELINE configs[3] and configs[4] at FULL size on one GPU (the bench line uses a configs[4] shard of 12 500).
+"""BASELINE configs[3] and configs[4] at FULL size on one GPU, through posterior="auto" (K-F / incremental) and through
+the O(n^2) kernel (posterior="full"), with the pick sequences of the two compared trial by trial.
 
     python tools/full_configs.py            -> gpurun_out/full_configs.json
 configs[3]: 10 000 trials over the 16 Wildcat Wells families, fixed theta, 200 x 200 lattice (step 0.5), 100 iterations.
@@ -20,11 +21,11 @@ S = 256
 surf = gen.wildcatwells_batch([s // 16 for s in range(S)], [bench.FAMILIES[s % 16][0] for s in range(S)],
                               [bench.FAMILIES[s % 16][1] for s in range(S)], device=dev)
 theta = torch.tensor(bench.THETA, dtype=torch.float64, device=dev)
-rng = np.random.default_rng(1)
 out = {}
+picks = {}
 
 
-def run(name, lat, T, iters):
+def run(name, lat, T, iters, posterior="full"):
     G = lat.G
     pts = lat.points(dev)
     if lat.h == 1.0:
@@ -32,11 +33,13 @@ def run(name, lat, T, iters):
     else:
         sidx = torch.arange(S, dtype=torch.int32, device=dev).repeat_interleave(G)
         obj = ops.wildcat_eval(surf.reshape(S, 101, 101), pts.repeat(S, 1), sidx).reshape(S, G).float().contiguous()
+    rng = np.random.default_rng(1)
     idx = torch.as_tensor(bench.init_sets(T, 10, 5) % G if G == 10000 else np.stack([rng.choice(G, 10, replace=False) for _ in range(T)]), device=dev)
     sid = torch.as_tensor((np.arange(T) % S).astype(np.int32), device=dev)
     X0 = pts[idx]
     y0 = obj[sid.long()[:, None], idx].double()
-    bo = engine.BatchedBO(pts, obj, sid, X0, y0, iters, theta=theta, tol=-1.0, lattice=lat, check_every=0)
+    bo = engine.BatchedBO(pts, obj, sid, X0, y0, iters, theta=theta, tol=-1.0, lattice=lat, check_every=0, posterior=posterior)
+    path = "persistent" if bo.persistent else ("incremental" if bo.incremental else "full")
     torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(); res = bo.run(); e1.record(); torch.cuda.synchronize()
@@ -44,7 +47,8 @@ def run(name, lat, T, iters):
     nit = int(res.nit.sum())
     flops = sum(T * G * (n * n + 17 * n + 30) for n in range(10, 10 + iters))
     gap = (100 - res.yall[:, -1]).mean().item()
-    out[name] = {"trials": T, "grid": f"{lat.Gx}x{lat.Gy}", "iterations": iters, "seconds": sec, "bo_iterations_per_s": nit / sec,
+    picks[name] = res.picked.clone()
+    out[name] = {"trials": T, "grid": f"{lat.Gx}x{lat.Gy}", "iterations": iters, "posterior": path, "seconds": sec, "bo_iterations_per_s": nit / sec,
                  "F_B_tflops_per_s": flops / sec / 1e12, "mean_final_gap": gap, "status_bits": int(res.status.max()),
                  "mem_allocated_GB": torch.cuda.max_memory_allocated() / 1e9}
     print(name, out[name], flush=True)
@@ -52,6 +56,11 @@ def run(name, lat, T, iters):
     torch.cuda.empty_cache()
 
 
-run("configs[3]_full_10000_trials_200x200", ops.Lattice(200, 200, 0.0, 0.0, 0.5), 10000, 100)
-run("configs[4]_full_100000_trials_100x100_one_gpu", ops.Lattice(100, 100), 100000, 100)
+for post in ("auto", "full"):
+    run(f"configs[3]_full_10000_trials_200x200_{post}", ops.Lattice(200, 200, 0.0, 0.0, 0.5), 10000, 100, post)
+    run(f"configs[4]_full_100000_trials_100x100_one_gpu_{post}", ops.Lattice(100, 100), 100000, 100, post)
+for c in ("configs[3]_full_10000_trials_200x200", "configs[4]_full_100000_trials_100x100_one_gpu"):
+    same = (picks[c + "_auto"] == picks[c + "_full"]).all(dim=1)
+    out[c + "_trials_with_identical_picks_auto_vs_full"] = [int(same.sum()), int(same.numel())]
+    print(c, "identical pick sequences:", int(same.sum()), "of", int(same.numel()), flush=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "full_configs.json"), "w"), indent=1)
