@@ -266,3 +266,20 @@ def test_window_draw_consumes_the_generator_like_the_reference():
         acquired_b.append(loc)
         assert loc == loc_ref
     assert a.integers(0, 1 << 30) == b.integers(0, 1 << 30)            # both generators are at the same position
+
+
+def test_bench_contract_helpers():
+    """bench.py host helpers: both arms print the SAME config (the driver compares them), configs[4] is strong-scaled by
+    default (the same 100 000 trials at every N), initial sets are distinct inside a set and a function of the seed."""
+    import argparse
+    import bench
+    args = argparse.Namespace(trials=100000, trials_per_gpu=0, iters=100, n0=10, surfaces=256, gpus=4)
+    assert bench.total_trials(args, 4) == (100000, True) and bench.total_trials(args, 1) == (100000, True)
+    assert bench.workload_config(args, 4) == bench.workload_config(args, max(1, args.gpus))
+    assert bench.workload_config(args, 4)["trials_total"] == 100000
+    weak = argparse.Namespace(**{**vars(args), "trials_per_gpu": 12500})
+    assert bench.total_trials(weak, 8) == (100000, False)
+    a, b = bench.init_sets(500, 10, 3), bench.init_sets(500, 10, 3)
+    assert np.array_equal(a, b) and a.shape == (500, 10) and a.min() >= 0 and a.max() < 10000
+    assert all(len(set(row)) == 10 for row in a)
+    assert not np.array_equal(a, bench.init_sets(500, 10, 4))
