@@ -322,7 +322,7 @@ def run_b200(args):
     nit_sum = int(res.nit.sum().item())
     status_max = int(res.status.max().item())
     picked_headline = res.picked[:1480].clone()
-    for _ in range(1):
+    for _ in range(2):                                       # allocator / lazy-module warm-up of the host-facing entry
         step_e2e()
     ms_e2e, (res_e2e, _) = timed(step_e2e, args.steps)
     e2e_same = bool(torch.equal(res_e2e.yall[lo:hi], res.yall))
